@@ -1,0 +1,244 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front-end to the two CPU oracles.
+
+* ``Oracle``    -- oracle/libimhd_oracle.so, the C restatement (oracle/imhd_oracle.c).
+* ``Reference`` -- oracle/_ref/libimhd_ref_cpu.so, the reference's own unmodified kernel
+  sources compiled for the host (oracle/Makefile ``ref``; needs /root/reference to BUILD,
+  the prebuilt .so travels to the GPU box).
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's ``cpu_baseline`` / ``--impl
+reference`` legs may import this module; the product package never does.
+
+All arrays are numpy float32, C-contiguous, shape (8, Nz, Nx, Ny) == the reference's IDX3D
+layout l = k*Nx*Ny + i*Ny + j with variable v at l + v*Nx*Ny*Nz
+(/root/reference/lib/on-device/kernels_od.cu:11,16).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PATH_A, PATH_B = 0, 1
+VARS = ("rho", "rhovx", "rhovy", "rhovz", "Bx", "By", "Bz", "e")
+
+_f, _i, _p = C.c_float, C.c_int, C.c_void_p
+
+
+def build(ref: bool | None = None) -> None:
+    """(Re)build the oracle libraries.  ``ref=None`` builds _ref only where /root/reference exists."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+    if ref is None:
+        ref = os.path.isdir("/root/reference/lib/on-device")
+    if ref:
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+
+
+def _ptr(a: np.ndarray):
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"], "float32 C-contiguous arrays only"
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def grid_spacing(lo: float, hi: float, n: int) -> np.float32:
+    """dx = (x_max - x_min)/(Nx-1) in fp32, as main.cu:98-100 / no_diffusion.cu:106-108."""
+    return np.float32((np.float32(hi) - np.float32(lo)) / np.float32(n - 1))
+
+
+class _Lib:
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing -- run `make -C oracle`")
+        self.lib = C.CDLL(path)
+
+    def _sig(self, name, argtypes):
+        fn = getattr(self.lib, name)
+        fn.argtypes, fn.restype = argtypes, None
+        return fn
+
+
+class Oracle(_Lib):
+    """The C restatement (always available: built from this repo alone)."""
+
+    kind = "port"
+
+    def __init__(self):
+        super().__init__(os.path.join(HERE, "libimhd_oracle.so"))
+        s = self._sig
+        dims = [_i, _i, _i]
+        s("oracle_predictor", [_p, _p, _i, _f, _f, _f, _f, _f] + dims)
+        s("oracle_corrector_nodiff", [_p, _p, _f, _f, _f, _f] + dims)
+        s("oracle_pbcs", [_p] + dims)
+        s("oracle_wall_bcs_leftright", [_p] + dims)
+        s("oracle_corrector_diff", [_p, _p, _f, _f, _f, _f, _f] + dims)
+        s("oracle_boundary_conditions", [_p, _p, _f, _f, _f, _f, _f] + dims)
+        s("oracle_prime", [_p, _p, _i, _f, _f, _f, _f, _f] + dims)
+        s("oracle_steps", [_p, _p, _i, _i, _f, _f, _f, _f, _f] + dims)
+        s("oracle_init_grids", [_p, _p, _p] + [_f] * 6 + dims)
+        s("oracle_screwpinch_stride", [_p, _f, _p, _p, _p] + dims)
+        s("oracle_cubic_bennett_vortex_m0", [_p, _f, _f, _p, _p, _p] + dims)
+
+    # Q arrays have shape (8, Nz, Nx, Ny)
+    @staticmethod
+    def _dims(Q):
+        _, Nz, Nx, Ny = Q.shape
+        return Nx, Ny, Nz
+
+    def init_grids(self, bounds, Nx, Ny, Nz):
+        x, y, z = (np.empty(n, np.float32) for n in (Nx, Ny, Nz))
+        self.lib.oracle_init_grids(_ptr(x), _ptr(y), _ptr(z), *[float(b) for b in bounds], Nx, Ny, Nz)
+        return x, y, z
+
+    def screwpinch_stride(self, J0, x, y, z):
+        Q = np.empty((8, len(z), len(x), len(y)), np.float32)
+        self.lib.oracle_screwpinch_stride(_ptr(Q), J0, _ptr(x), _ptr(y), _ptr(z), len(x), len(y), len(z))
+        return Q
+
+    def cubic_bennett_vortex_m0(self, k, A, x, y, z):
+        Q = np.empty((8, len(z), len(x), len(y)), np.float32)
+        self.lib.oracle_cubic_bennett_vortex_m0(_ptr(Q), k, A, _ptr(x), _ptr(y), _ptr(z), len(x), len(y), len(z))
+        return Q
+
+    def predictor(self, Q, Qint, path, D, dt, dx, dy, dz):
+        self.lib.oracle_predictor(_ptr(Q), _ptr(Qint), path, D, dt, dx, dy, dz, *self._dims(Q))
+
+    def corrector(self, Q, Qint, path, D, dt, dx, dy, dz):
+        """Corrector + fluid boundary pass, in place (A: FluidAdvanceLocalNoDiff + PBCs; B: FluidAdvanceLocal + BoundaryConditions)."""
+        d = self._dims(Q)
+        if path == PATH_A:
+            self.lib.oracle_corrector_nodiff(_ptr(Q), _ptr(Qint), dt, dx, dy, dz, *d)
+            self.lib.oracle_pbcs(_ptr(Q), *d)
+        else:
+            self.lib.oracle_corrector_diff(_ptr(Q), _ptr(Qint), D, dt, dx, dy, dz, *d)
+            self.lib.oracle_boundary_conditions(_ptr(Q), _ptr(Qint), D, dt, dx, dy, dz, *d)
+
+    def corrector_volume(self, Q, Qint, path, D, dt, dx, dy, dz):
+        d = self._dims(Q)
+        if path == PATH_A:
+            self.lib.oracle_corrector_nodiff(_ptr(Q), _ptr(Qint), dt, dx, dy, dz, *d)
+        else:
+            self.lib.oracle_corrector_diff(_ptr(Q), _ptr(Qint), D, dt, dx, dy, dz, *d)
+
+    def fluid_bcs(self, Q, Qint, path, D, dt, dx, dy, dz):
+        d = self._dims(Q)
+        if path == PATH_A:
+            self.lib.oracle_pbcs(_ptr(Q), *d)
+        else:
+            self.lib.oracle_boundary_conditions(_ptr(Q), _ptr(Qint), D, dt, dx, dy, dz, *d)
+
+    def wall_bcs_leftright(self, Q):
+        self.lib.oracle_wall_bcs_leftright(_ptr(Q), *self._dims(Q))
+
+    def pbcs(self, Q):
+        self.lib.oracle_pbcs(_ptr(Q), *self._dims(Q))
+
+    def prime(self, Q, Qint, path, D, dt, dx, dy, dz):
+        self.lib.oracle_prime(_ptr(Q), _ptr(Qint), path, D, dt, dx, dy, dz, *self._dims(Q))
+
+    def steps(self, Q, Qint, path, nsteps, D, dt, dx, dy, dz):
+        self.lib.oracle_steps(_ptr(Q), _ptr(Qint), path, nsteps, D, dt, dx, dy, dz, *self._dims(Q))
+
+
+class Reference(_Lib):
+    """The reference's own kernels run on the host (oracle/_ref)."""
+
+    kind = "reference"
+
+    def __init__(self, threads: int | None = None):
+        super().__init__(os.path.join(HERE, "_ref", "libimhd_ref_cpu.so"))
+        self.T = threads or (os.cpu_count() or 1)
+        s = self._sig
+        dims = [_i, _i, _i]
+        s("ref_init_grids", [_p, _p, _p] + [_f] * 6 + dims)
+        s("ref_screwpinch_stride", [_p, _f, _p, _p, _p] + dims + [_i])
+        s("ref_cubic_bennett_vortex_m0", [_p, _f, _f, _p, _p, _p] + dims + [_i])
+        s("ref_wall_bcs_leftright", [_p] + dims)
+        s("ref_wall_bcs_topbottom", [_p] + dims)
+        s("ref_pbcs", [_p] + dims)
+        s("ref_predictor_nodiff", [_p, _p, _f, _f, _f, _f] + dims + [_i])
+        s("ref_qint_bdry_nodiff", [_p, _p, _f, _f, _f, _f] + dims)
+        s("ref_corrector_nodiff", [_p, _p, _f, _f, _f, _f] + dims + [_i])
+        s("ref_predictor_stride", [_p, _p, _f, _f, _f, _f, _f] + dims + [_i])
+        s("ref_qint_boundary", [_p, _p, _f, _f, _f, _f, _f] + dims + [_i])
+        s("ref_corrector_diff", [_p, _p, _f, _f, _f, _f, _f] + dims + [_i])
+        s("ref_boundary_conditions", [_p, _p, _f, _f, _f, _f, _f] + dims)
+        s("ref_pathA_prime", [_p, _p, _f, _f, _f, _f] + dims + [_i])
+        s("ref_pathA_steps", [_p, _p, _i, _f, _f, _f, _f] + dims + [_i])
+        s("ref_pathB_prime", [_p, _p, _f, _f, _f, _f, _f] + dims + [_i])
+        s("ref_pathB_steps", [_p, _p, _i, _f, _f, _f, _f, _f] + dims + [_i])
+
+    _dims = staticmethod(Oracle._dims)
+
+    def init_grids(self, bounds, Nx, Ny, Nz):
+        x, y, z = (np.empty(n, np.float32) for n in (Nx, Ny, Nz))
+        self.lib.ref_init_grids(_ptr(x), _ptr(y), _ptr(z), *[float(b) for b in bounds], Nx, Ny, Nz)
+        return x, y, z
+
+    def screwpinch_stride(self, J0, x, y, z):
+        Q = np.empty((8, len(z), len(x), len(y)), np.float32)
+        self.lib.ref_screwpinch_stride(_ptr(Q), J0, _ptr(x), _ptr(y), _ptr(z), len(x), len(y), len(z), self.T)
+        return Q
+
+    def cubic_bennett_vortex_m0(self, k, A, x, y, z):
+        Q = np.empty((8, len(z), len(x), len(y)), np.float32)
+        self.lib.ref_cubic_bennett_vortex_m0(_ptr(Q), k, A, _ptr(x), _ptr(y), _ptr(z), len(x), len(y), len(z), self.T)
+        return Q
+
+    def predictor(self, Q, Qint, path, D, dt, dx, dy, dz, full=False):
+        d = self._dims(Q)
+        if path == PATH_A:
+            self.lib.ref_predictor_nodiff(_ptr(Q), _ptr(Qint), dt, dx, dy, dz, *d, self.T)
+            self.lib.ref_qint_bdry_nodiff(_ptr(Q), _ptr(Qint), dt, dx, dy, dz, *d)
+        else:
+            self.lib.ref_predictor_stride(_ptr(Q), _ptr(Qint), D, dt, dx, dy, dz, *d, self.T)
+            self.lib.ref_qint_boundary(_ptr(Q), _ptr(Qint), D, dt, dx, dy, dz, *d, int(full))
+
+    def corrector(self, Q, Qint, path, D, dt, dx, dy, dz):
+        d = self._dims(Q)
+        if path == PATH_A:
+            self.lib.ref_corrector_nodiff(_ptr(Q), _ptr(Qint), dt, dx, dy, dz, *d, self.T)
+            self.lib.ref_pbcs(_ptr(Q), *d)
+        else:
+            self.lib.ref_corrector_diff(_ptr(Q), _ptr(Qint), D, dt, dx, dy, dz, *d, self.T)
+            self.lib.ref_boundary_conditions(_ptr(Q), _ptr(Qint), D, dt, dx, dy, dz, *d)
+
+    def wall_bcs_leftright(self, Q):
+        self.lib.ref_wall_bcs_leftright(_ptr(Q), *self._dims(Q))
+
+    def wall_bcs_topbottom(self, Q):
+        self.lib.ref_wall_bcs_topbottom(_ptr(Q), *self._dims(Q))
+
+    def pbcs(self, Q):
+        self.lib.ref_pbcs(_ptr(Q), *self._dims(Q))
+
+    def prime(self, Q, Qint, path, D, dt, dx, dy, dz):
+        d = self._dims(Q)
+        if path == PATH_A:
+            self.lib.ref_pathA_prime(_ptr(Q), _ptr(Qint), dt, dx, dy, dz, *d, self.T)
+        else:
+            self.lib.ref_pathB_prime(_ptr(Q), _ptr(Qint), D, dt, dx, dy, dz, *d, self.T)
+
+    def steps(self, Q, Qint, path, nsteps, D, dt, dx, dy, dz):
+        d = self._dims(Q)
+        if path == PATH_A:
+            self.lib.ref_pathA_steps(_ptr(Q), _ptr(Qint), nsteps, dt, dx, dy, dz, *d, self.T)
+        else:
+            self.lib.ref_pathB_steps(_ptr(Q), _ptr(Qint), nsteps, D, dt, dx, dy, dz, *d, self.T)
+
+
+def best_available():
+    """The strongest oracle present: the reference itself if its .so was built, else the restatement."""
+    try:
+        return Reference()
+    except (FileNotFoundError, OSError):
+        return Oracle()
+
+
+def normalised_linf(new: np.ndarray, ref: np.ndarray) -> np.ndarray:
+    """Per-variable max|new-ref| / max|ref| over the full array."""
+    n = new.reshape(8, -1).astype(np.float64)
+    r = ref.reshape(8, -1).astype(np.float64)
+    den = np.abs(r).max(axis=1)
+    den[den == 0] = 1.0
+    return np.abs(n - r).max(axis=1) / den
