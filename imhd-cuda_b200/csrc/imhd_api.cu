@@ -1,0 +1,246 @@
+// libimhd_b200: library plumbing (errors, launch counter) and the context API the drop-in
+// drivers call.  Host time loop replaces src/on-device/main.cu:196-238 and
+// src/on-device/no_diffusion.cu:284-337: no per-phase cudaDeviceSynchronize, no per-step
+// blocking D2H, one fused kernel per step on a single stream.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <new>
+
+#include "imhd_common.cuh"
+
+namespace imhd {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    // same information as the reference's checkCuda (include/on-device/utils/utils.cuh:8-16),
+    // but returned instead of exit()
+    set_error("GPUassert: %s (%s) %s %d", cudaGetErrorString(e), what, file, line);
+    return (int)e;
+}
+
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace imhd
+
+using namespace imhd;
+
+struct imhd_ctx {
+    int Nx, Ny, Nz, device;
+    size_t cells;
+    float* buf[2];  // ping-pong state buffers; buf[cur] holds Q^n.  buf[1-cur] is the reference's `intvars`
+                    // allocation: Qint for the granular path, Q^{n+1} for the fused path.
+    int cur;
+    float *gx, *gy, *gz;       // device grids
+    float* qint_planes;        // 2 x (8,Nx,Ny): predictor planes for the periodic wrap
+    cudaStream_t stream;
+    bool have_grids, primed, qint_valid;
+    int path;
+    float D, dt, dx, dy, dz, corner_e;
+    float bounds[6];
+};
+
+extern "C" int imhd_abi_version(void) { return 1; }
+extern "C" const char* imhd_last_error(void) { return g_err; }
+extern "C" uint64_t imhd_launch_count(void) { return g_launches.load(); }
+
+extern "C" imhd_ctx* imhd_create(int Nx, int Ny, int Nz, int device) {
+    if (bad_dims(Nx, Ny, Nz)) return nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("imhd_create: no usable CUDA device (%s); this library has no CPU path",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { set_error("imhd_create: device %d out of range [0,%d)", device, ndev); return nullptr; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__); return nullptr; }
+    imhd_ctx* c = new (std::nothrow) imhd_ctx();
+    if (!c) { set_error("imhd_create: out of host memory"); return nullptr; }
+    memset(c, 0, sizeof(*c));
+    c->Nx = Nx; c->Ny = Ny; c->Nz = Nz; c->device = device;
+    c->cells = (size_t)Nx * Ny * Nz;
+    const size_t bytes = 8 * c->cells * sizeof(float);
+    bool ok = cudaMalloc(&c->buf[0], bytes) == cudaSuccess && cudaMalloc(&c->buf[1], bytes) == cudaSuccess &&
+              cudaMalloc(&c->gx, sizeof(float) * Nx) == cudaSuccess && cudaMalloc(&c->gy, sizeof(float) * Ny) == cudaSuccess &&
+              cudaMalloc(&c->gz, sizeof(float) * Nz) == cudaSuccess &&
+              cudaMalloc(&c->qint_planes, 2 * 8 * sizeof(float) * (size_t)Nx * Ny) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) {
+        cuda_fail(cudaGetLastError(), "imhd_create allocation", __FILE__, __LINE__);
+        imhd_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+extern "C" void imhd_destroy(imhd_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    cudaFree(c->buf[0]); cudaFree(c->buf[1]);
+    cudaFree(c->gx); cudaFree(c->gy); cudaFree(c->gz); cudaFree(c->qint_planes);
+    delete c;
+}
+
+#define CTX_CHECK(c)                                                  \
+    do {                                                              \
+        if (!(c)) { set_error("null context"); return IMHD_E_INVALID; } \
+        IMHD_CUDA(cudaSetDevice((c)->device));                        \
+    } while (0)
+
+extern "C" int imhd_ctx_init_grids(imhd_ctx* c, float x_min, float x_max, float y_min, float y_max, float z_min,
+                                   float z_max) {
+    CTX_CHECK(c);
+    const float b[6] = {x_min, x_max, y_min, y_max, z_min, z_max};
+    memcpy(c->bounds, b, sizeof(b));
+    // fp32, as main.cu:98-100 / no_diffusion.cu:106-108
+    c->dx = (x_max - x_min) / (c->Nx - 1);
+    c->dy = (y_max - y_min) / (c->Ny - 1);
+    c->dz = (z_max - z_min) / (c->Nz - 1);
+    if (int e = imhd_init_grids(c->gx, c->gy, c->gz, x_min, x_max, y_min, y_max, z_min, z_max, c->Nx, c->Ny, c->Nz, c->stream))
+        return e;
+    c->have_grids = true;
+    return 0;
+}
+
+static int need_grids(imhd_ctx* c) {
+    if (!c->have_grids) { set_error("initial condition requested before imhd_ctx_init_grids"); return IMHD_E_STATE; }
+    return 0;
+}
+
+extern "C" int imhd_ctx_init_screwpinch_stride(imhd_ctx* c, float J0) {
+    CTX_CHECK(c);
+    if (int e = need_grids(c)) return e;
+    c->primed = false;
+    return imhd_init_screwpinch_stride(c->buf[c->cur], J0, c->gx, c->gy, c->gz, c->Nx, c->Ny, c->Nz, c->stream);
+}
+
+extern "C" int imhd_ctx_init_cubic_bennett_vortex_m0(imhd_ctx* c, float k, float A) {
+    CTX_CHECK(c);
+    if (int e = need_grids(c)) return e;
+    c->primed = false;
+    return imhd_init_cubic_bennett_vortex_m0(c->buf[c->cur], k, A, c->gx, c->gy, c->gz, c->Nx, c->Ny, c->Nz, c->stream);
+}
+
+extern "C" int imhd_ctx_set_state(imhd_ctx* c, const float* host_Q) {
+    CTX_CHECK(c);
+    if (!host_Q) { set_error("imhd_ctx_set_state: null host buffer"); return IMHD_E_INVALID; }
+    c->primed = false;
+    IMHD_CUDA(cudaMemcpyAsync(c->buf[c->cur], host_Q, 8 * c->cells * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+extern "C" int imhd_ctx_set_spacing(imhd_ctx* c, float dx, float dy, float dz) {
+    CTX_CHECK(c);
+    c->dx = dx; c->dy = dy; c->dz = dz;
+    return 0;
+}
+
+extern "C" int imhd_ctx_prime(imhd_ctx* c, int path, float D, float dt) {
+    CTX_CHECK(c);
+    if (path != IMHD_PATH_A && path != IMHD_PATH_B) { set_error("imhd_ctx_prime: bad path %d", path); return IMHD_E_INVALID; }
+    if (!(c->dx > 0.f) || !(c->dy > 0.f) || !(c->dz > 0.f)) {
+        set_error("imhd_ctx_prime: grid spacing unset (call imhd_ctx_init_grids or imhd_ctx_set_spacing)");
+        return IMHD_E_STATE;
+    }
+    c->path = path; c->D = D; c->dt = dt;
+    // no_diffusion.cu:174-177: wall BCs + PBCs on the initial state (path A only; main.cu applies none)
+    if (path == IMHD_PATH_A)
+        if (int e = imhd_initial_bcs(c->buf[c->cur], c->Nx, c->Ny, c->Nz, c->stream)) return e;
+    // The reference also computes Qint^0 here (no_diffusion.cu:183-199 / main.cu:108-111).  Qint is a pure
+    // function of Q, so the fused path recomputes it on chip every step and the granular
+    // path computes it lazily at the start of a step.
+    c->corner_e = 0.0f;
+    if (path == IMHD_PATH_B) {  // the column (Nx-1,Ny-1) holds this wall value at k=0 and k=Nz-1 from step 1 on (B-8)
+        float e0 = 0.0f;
+        const size_t l = (size_t)(c->Nx - 1) * c->Ny + (c->Ny - 1);
+        IMHD_CUDA(cudaMemcpyAsync(&e0, c->buf[c->cur] + l + 7 * c->cells, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        IMHD_CUDA(cudaStreamSynchronize(c->stream));
+        c->corner_e = imhd_wall_energy_fixed_point(e0, c->Nx);
+    }
+    c->qint_valid = false;
+    c->primed = true;
+    return 0;
+}
+
+extern "C" int imhd_ctx_step_granular(imhd_ctx* c, int nsteps) {
+    CTX_CHECK(c);
+    if (!c->primed) { set_error("imhd_ctx_step_granular before imhd_ctx_prime"); return IMHD_E_STATE; }
+    float* Q = c->buf[c->cur];
+    float* Qi = c->buf[1 - c->cur];
+    for (int s = 0; s < nsteps; ++s) {
+        if (!c->qint_valid)
+            if (int e = imhd_predictor(Q, Qi, c->path, c->D, c->dt, c->dx, c->dy, c->dz, c->Nx, c->Ny, c->Nz, c->stream)) return e;
+        if (int e = imhd_corrector(Q, Qi, c->path, c->D, c->dt, c->dx, c->dy, c->dz, c->Nx, c->Ny, c->Nz, c->stream)) return e;
+        if (int e = imhd_fluid_bcs(Q, Qi, c->path, c->D, c->dt, c->dx, c->dy, c->dz, c->Nx, c->Ny, c->Nz, c->stream)) return e;
+        c->qint_valid = false;
+    }
+    return 0;
+}
+
+extern "C" int imhd_ctx_step(imhd_ctx* c, int nsteps) {
+    CTX_CHECK(c);
+    if (!c->primed) { set_error("imhd_ctx_step before imhd_ctx_prime"); return IMHD_E_STATE; }
+    imhd_slab s;
+    s.Nx = c->Nx; s.Ny = c->Ny; s.Nz = c->Nz; s.k0 = 0; s.nzl = c->Nz; s.ghosts = 0;
+    s.path = c->path; s.D = c->D; s.dt = c->dt; s.dx = c->dx; s.dy = c->dy; s.dz = c->dz; s.corner_e = c->corner_e;
+    const size_t pl8 = 8 * (size_t)c->Nx * c->Ny;
+    for (int st = 0; st < nsteps; ++st) {
+        const float* Qin = c->buf[c->cur];
+        float* Qout = c->buf[1 - c->cur];
+        // periodic wrap: Qint(-1) == Qint(Nz-2) and Qint(Nz-1) == Qint(0)
+        if (int e = imhd_qint_plane(Qin, c->qint_planes, c->Nz - 2, &s, c->stream)) return e;
+        if (int e = imhd_qint_plane(Qin, c->qint_planes + pl8, 0, &s, c->stream)) return e;
+        if (int e = imhd_step_fused(Qin, Qout, c->qint_planes, c->qint_planes + pl8, &s, c->stream)) return e;
+        c->cur = 1 - c->cur;
+    }
+    c->qint_valid = false;
+    return 0;
+}
+
+extern "C" int imhd_ctx_get_state(imhd_ctx* c, float* host_Q) {
+    CTX_CHECK(c);
+    if (!host_Q) { set_error("imhd_ctx_get_state: null host buffer"); return IMHD_E_INVALID; }
+    IMHD_CUDA(cudaMemcpyAsync(host_Q, c->buf[c->cur], 8 * c->cells * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    IMHD_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int imhd_ctx_get_grids(imhd_ctx* c, float* x, float* y, float* z) {
+    CTX_CHECK(c);
+    if (int e = need_grids(c)) return e;
+    IMHD_CUDA(cudaMemcpyAsync(x, c->gx, sizeof(float) * c->Nx, cudaMemcpyDeviceToHost, c->stream));
+    IMHD_CUDA(cudaMemcpyAsync(y, c->gy, sizeof(float) * c->Ny, cudaMemcpyDeviceToHost, c->stream));
+    IMHD_CUDA(cudaMemcpyAsync(z, c->gz, sizeof(float) * c->Nz, cudaMemcpyDeviceToHost, c->stream));
+    IMHD_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" float* imhd_ctx_device_state(imhd_ctx* c) { return c ? c->buf[c->cur] : nullptr; }
+extern "C" void* imhd_ctx_stream(imhd_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+extern "C" int imhd_ctx_synchronize(imhd_ctx* c) {
+    CTX_CHECK(c);
+    IMHD_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int imhd_run_host(imhd_ctx* c, const float* host_Q_in, float* host_Q_out, int path, float D, float dt,
+                             float dx, float dy, float dz, int nsteps) {
+    CTX_CHECK(c);
+    if (int e = imhd_ctx_set_state(c, host_Q_in)) return e;
+    if (int e = imhd_ctx_set_spacing(c, dx, dy, dz)) return e;
+    if (int e = imhd_ctx_prime(c, path, D, dt)) return e;
+    if (int e = imhd_ctx_step(c, nsteps)) return e;
+    return imhd_ctx_get_state(c, host_Q_out);
+}

@@ -1,0 +1,454 @@
+// Fused time step: ONE sweep Q^n -> Q^{n+1} per step.  Predictor (all cell classes), corrector,
+// diffusion and every boundary pass of one reference time step (main.cu:200-213 /
+// no_diffusion.cu:288-311) are evaluated on chip; the intermediate state Qint never touches HBM
+// (it is a pure function of Q: SURVEY.md A.3).  Algorithmic traffic: read 8 + write 8 fp32 per
+// cell-update = 64 B.
+//
+// Decomposition
+//   - thread block = TI x 32 threads; threadIdx.x (a warp) runs along j, the unit-stride axis of
+//     the reference layout, threadIdx.y along i.  Each thread owns ONE (i,j) column and marches
+//     along k over a z-chunk, keeping a register queue of the column: Q(k), Q(k+1), H(Q(k+1)),
+//     Qint(k-1), Qint(k).
+//   - per plane, every thread publishes Q(k+1) and Qint(k) of its column once; i+-1 neighbours
+//     are read back from shared memory (double buffered -> one __syncthreads per plane), j+-1
+//     neighbours come from warp shuffles.
+//   - the outer ring of the tile (1 cell for path A, 2 for path B) only feeds its neighbours;
+//     out-of-domain threads idle.  Tiles overlap by that ring.
+//   - z is cut into chunks for load balance; a chunk re-derives Qint(ka-1), Qint(ka) in two
+//     warm-up planes.  At slab ends the predictor plane just outside the slab comes from the
+//     qint_lo / qint_hi buffers (periodic wrap on one GPU, neighbour rank on several).
+//
+// Arithmetic: the "fast" recipe of imhd_math.cuh (fp32 fluxes, one reciprocal per state), with the
+// O(1) sums arranged to round where the reference rounds (DESIGN.md "Precision").  The k=0 face of
+// path B (1 plane in Nz) uses the exact recipe.  The translation unit is compiled with
+// -fmad=false and every fused multiply-add is written out, so a value depends only on its inputs,
+// never on which kernel/block computed it: results are bit-identical for any chunking or slab
+// decomposition.
+#include "imhd_common.cuh"
+
+namespace imhd {
+
+struct FusedArgs {
+    const float* Qin;   // variable 0, array plane 0
+    float* Qout;
+    long long vs;       // variable stride of Qin/Qout in floats
+    int kbase;          // global plane index held by array plane 0
+    int kmin, kmax;     // global planes that may be READ from Qin: [kmin, kmax]
+    int k0, k1;         // owned (written) global planes [k0, k1)
+    const float* qlo;   // (8,Nx,Ny) Qint at global plane lo_plane (k0-1; Nz-2 data when k0 == 0)
+    const float* qhi;   // (8,Nx,Ny) Qint at global plane hi_plane = min(k1, Nz-1)
+    int hi_plane;
+    int chunk;          // owned planes per z-chunk
+    int ntile_i, ntile_j;
+    float corner_e;     // path B: fixed-point wall energy of column (Nx-1,Ny-1) (B-8)
+    Params P;
+};
+
+template <int PATH>
+struct Ring {  // halo ring width of a tile
+    static constexpr int O = PATH == IMHD_PATH_A ? 1 : 2;
+};
+
+__device__ __forceinline__ void ldg8(const float* __restrict__ A, long long off, long long vs, float U[8]) {
+#pragma unroll
+    for (int v = 0; v < 8; ++v) U[v] = __ldg(A + off + v * vs);
+}
+
+__device__ __forceinline__ void hflux(const float U[8], float h[8]) {
+    flux_indexed<false, DIR_Z>(U, make_aux<false>(U), h);
+}
+
+// -----------------------------------------------------------------------------------------------
+// Predictor at one cell from raw states (fast recipe).  c = Q(i,j,k), xp = Q(i+1,j,k),
+// yp = Q(i,j+1,k), hc = H(Q(i,j,k)), hp = H(Q(i,j,k+1)); xm, ym, zm, zp only when `lap`.
+// Cell classes and typos: kernels_od_intvar.cu:1160-1253, kernels_intvarbcs.cu:560-1110 (B-15).
+// -----------------------------------------------------------------------------------------------
+template <int PATH>
+__device__ __forceinline__ void qint_cell(const float c[8], const float xp[8], const float yp[8], const float hc[8],
+                                          const float hp[8], const float xm[8], const float ym[8], const float zm[8],
+                                          const float zp[8], bool bottom, bool right, bool front, bool lap,
+                                          const Params& P, float out[8]) {
+    const Aux<false> a = make_aux<false>(c);
+    float f[8], g[8], t[8], dF[8], dG[8], dH[8];
+    flux_indexed<false, DIR_X>(c, a, f);
+    flux_indexed<false, DIR_Y>(c, a, g);
+    flux_indexed<false, DIR_X>(xp, make_aux<false>(xp), t);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) dF[v] = bottom ? -f[v] : t[v] - f[v];
+    flux_indexed<false, DIR_Y>(yp, make_aux<false>(yp), t);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) dG[v] = right ? -g[v] : t[v] - g[v];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) dH[v] = hp[v] - hc[v];
+    if (front && right && !bottom) dF[EN] = f[EN] - f[EN];
+    if (front && bottom && !right) {
+        dH[MZ] = hp[MZ] - g[MZ];
+        dH[EN] = hp[EN] - g[EN];
+        dG[BZ] = t[BZ] - t[BZ];
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        float base = c[v];
+        if (v == MZ && bottom && right) base = c[MX];
+        float r = fmaf(-P.tz, dH[v], fmaf(-P.ty, dG[v], fmaf(-P.tx, dF[v], base)));
+        if (PATH == IMHD_PATH_B && lap)
+            r = fmaf(P.dt, num_diff<false>(c[v], xp[v], yp[v], zp[v], xm[v], ym[v], zm[v], P.D, P.dc), r);
+        out[v] = r;
+    }
+}
+
+// -----------------------------------------------------------------------------------------------
+// Corrector at one cell (fast recipe).  q = Q(i,j,k); c, xm, ym, zm = Qint at the cell and at
+// i-1, j-1, k-1; xp, yp, zp = Qint at i+1, j+1, k+1 (path B diffusion only).
+// kernels_od.cu:378-522 / :120-345, LaxWendroffAdv*Local :1206-1332, quirks B-4, B-5, B-6.
+// -----------------------------------------------------------------------------------------------
+template <int PATH>
+__device__ __forceinline__ void corr_cell(const float q[8], const float c[8], const float xm[8], const float ym[8],
+                                          const float zm[8], const float xp[8], const float yp[8], const float zp[8],
+                                          const Params& P, float out[8]) {
+    const Aux<false> ac = make_aux<false>(c), ai = make_aux<false>(xm), aj = make_aux<false>(ym);
+    const float invk = fast_rcp(zm[RHO]);
+    const float KEk = h_KE<false>(zm[RHO], zm[MX], zm[MY], zm[MZ], invk);
+    const float Bk = h_Bsq<false>(xm[BX], ym[BY], zm[BZ]);                                        // B-4
+    const float pk = h_p<false>(zm[EN], Bk, KEk);
+    const float Dk = h_Bdotu<false>(zm[RHO], zm[MX], ym[MY], zm[MZ], zm[BX], zm[BY], zm[BZ], invk);  // B-5
+    float fc[8], gc[8], hc[8], fi[8], gj[8], hk[8];
+    flux_local<false, DIR_X>(c, ac.p, ac.Bsq, ac.Bdotu, ac.invf, fc);
+    flux_local<false, DIR_Y>(c, ac.p, ac.Bsq, ac.Bdotu, ac.invf, gc);
+    flux_local<false, DIR_Z>(c, ac.p, ac.Bsq, ac.Bdotu, ac.invf, hc);
+    flux_local<false, DIR_X>(xm, ai.p, ai.Bsq, ai.Bdotu, ai.invf, fi);
+    flux_local<false, DIR_Y>(ym, aj.p, aj.Bsq, aj.Bdotu, aj.invf, gj);
+    flux_local<false, DIR_Z>(zm, pk, Bk, Dk, invk, hk);
+    if (PATH == IMHD_PATH_B) fi[RHO] = xm[RHO];  // B-6
+    const float hx = 0.5f * P.tx, hy = 0.5f * P.ty, hz = 0.5f * P.tz;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        const float dF = fc[v] - fi[v], dG = gc[v] - gj[v], dH = hc[v] - hk[v];
+        // reference: float(0.5*(q+c) - 0.5tx dF - 0.5ty dG - 0.5tz dH) with q+c an fp32 sum and the rest
+        // fp64.  0.5*s is exact and T is ~1e-2 of it, so one fp32 rounding of (0.5 s - T) reproduces it.
+        const float s = q[v] + c[v];
+        const float T = fmaf(hx, dF, fmaf(hy, dG, hz * dH));
+        float r = fmaf(0.5f, s, -T);
+        if (PATH == IMHD_PATH_B)
+            r = fmaf(P.dt, num_diff<false>(c[v], xp[v], yp[v], zp[v], xm[v], ym[v], zm[v], P.D, P.dc), r);
+        out[v] = r;
+    }
+}
+
+// Path B, k = 0 face (BoundaryConditions, kernels_fluidbcs.cu:52-116): corrector with INDEXED fluxes of
+// Qint, k-1 -> Nz-2, + dt*numericalDiffusionFront; exact recipe (1 plane in Nz, not worth a fast one).
+__device__ __noinline__ void front_cell_exact(const float q[8], const float c[8], const float xm[8], const float ym[8],
+                                              const float zm[8], const float xp[8], const float yp[8],
+                                              const float zp[8], const Params& P, float out[8]) {
+    float f[8], g[8], h[8], t[8], dF[8], dG[8], dH[8];
+    const Aux<true> a = make_aux<true>(c);
+    flux_indexed<true, DIR_X>(c, a, f);
+    flux_indexed<true, DIR_Y>(c, a, g);
+    flux_indexed<true, DIR_Z>(c, a, h);
+    flux_indexed<true, DIR_X>(xm, make_aux<true>(xm), t);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) dF[v] = f[v] - t[v];
+    flux_indexed<true, DIR_Y>(ym, make_aux<true>(ym), t);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) dG[v] = g[v] - t[v];
+    flux_indexed<true, DIR_Z>(zm, make_aux<true>(zm), t);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) dH[v] = h[v] - t[v];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        const float nd = num_diff<true>(c[v], xp[v], yp[v], zp[v], xm[v], ym[v], zm[v], P.D, P.dc);
+        const float pn = P.dt * nd;
+        out[v] = (float)(0.5 * (q[v] + c[v]) - 0.5 * P.tx * dF[v] - 0.5 * P.ty * dG[v] - 0.5 * P.tz * dH[v] + pn);
+    }
+}
+
+// -----------------------------------------------------------------------------------------------
+// The fused z-marching kernel.
+// -----------------------------------------------------------------------------------------------
+template <int PATH, int TI>
+__global__ void __launch_bounds__(TI * 32) k_fused_step(const FusedArgs A) {
+    constexpr int O = Ring<PATH>::O;
+    constexpr int WI = TI - 2 * O, WJ = 32 - 2 * O;
+    extern __shared__ float smem[];
+    // sQ[buf][v][ti][lane], then sQi[buf][v][ti][lane]
+    float* sQ = smem;
+    float* sQi = smem + 2 * 8 * TI * 32;
+
+    const Params& P = A.P;
+    const int lane = threadIdx.x, ti = threadIdx.y;
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    const int i = bi * WI + 1 - O + ti, j = bj * WJ + 1 - O + lane;
+    const bool in_dom = i >= 0 && i < P.Nx && j >= 0 && j < P.Ny;
+    const int ic = min(max(i, 0), P.Nx - 1), jc = min(max(j, 0), P.Ny - 1);
+    const long long lcol = (long long)ic * P.Ny + jc;
+    const bool top = (i == 0), bottom = (i == P.Nx - 1), left = (j == 0), right = (j == P.Ny - 1);
+    const bool interior_ij = in_dom && !top && !bottom && !left && !right;
+    // cells this thread writes: the tile's inner window, widened to the domain edge on edge tiles
+    const int oi_lo = bi == 0 ? 0 : 1 + bi * WI, oi_hi = bi == A.ntile_i - 1 ? P.Nx : 1 + (bi + 1) * WI;
+    const int oj_lo = bj == 0 ? 0 : 1 + bj * WJ, oj_hi = bj == A.ntile_j - 1 ? P.Ny : 1 + (bj + 1) * WJ;
+    const bool owner = in_dom && i >= oi_lo && i < oi_hi && j >= oj_lo && j < oj_hi;
+    // shared-memory slots of this thread and of its i-1 / i+1 rows
+    const int tim = max(ti - 1, 0), tip = min(ti + 1, TI - 1);
+
+    const int ka = A.k0 + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.k1);
+    const bool first = blockIdx.z == 0;
+    const int ks = first ? ka - 1 : ka - 2;
+
+    auto plane_off = [&](int k) -> long long {
+        const int kc = min(max(k, A.kmin), A.kmax);
+        return (long long)(kc - A.kbase) * P.plane + lcol;
+    };
+
+    float q0[8], q1[8], h1[8], qim[8], qic[8];
+    ldg8(A.Qin, plane_off(ks), A.vs, q0);
+    ldg8(A.Qin, plane_off(ks + 1), A.vs, q1);
+    hflux(q1, h1);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) { qim[v] = 1.0f; qic[v] = 1.0f; }
+    if (first && A.qlo != nullptr) ldg8(A.qlo, lcol, P.plane, qic);  // Qint(ks) == Qint(ka-1)
+
+    for (int k = ks; k < kb; ++k) {
+        const int buf = (k - ks) & 1;
+        const int kp = k + 1;
+        float qn[8], hn[8], qip[8];
+        ldg8(A.Qin, plane_off(k + 2), A.vs, qn);
+        float* bQ = sQ + buf * 8 * TI * 32;
+        float* bQi = sQi + buf * 8 * TI * 32;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            bQ[(v * TI + ti) * 32 + lane] = q1[v];
+            bQi[(v * TI + ti) * 32 + lane] = qic[v];
+        }
+        __syncthreads();
+
+        // ---- predictor plane kp = k+1 ------------------------------------------------------------
+        hflux(qn, hn);
+        if (kp == A.hi_plane) {
+            ldg8(A.qhi, lcol, P.plane, qip);
+        } else if (kp <= P.Nz - 2) {
+            float xp[8], yp[8], xm[8], ym[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                xp[v] = bQ[(v * TI + tip) * 32 + lane];
+                yp[v] = __shfl_down_sync(0xffffffffu, q1[v], 1);
+            }
+            const bool lap = PATH == IMHD_PATH_B && interior_ij && kp >= 1;
+            if (PATH == IMHD_PATH_B) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    xm[v] = bQ[(v * TI + tim) * 32 + lane];
+                    ym[v] = __shfl_up_sync(0xffffffffu, q1[v], 1);
+                }
+            }
+            qint_cell<PATH>(q1, xp, yp, h1, hn, xm, ym, q0, qn, bottom, right, kp == 0, lap, P, qip);
+        } else {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) qip[v] = 1.0f;
+        }
+
+        // ---- corrector plane k -----------------------------------------------------------------------
+        if (k >= ka) {
+            float out[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) out[v] = q0[v];  // cells no pass touches are carried over
+            float xm[8], ym[8], xp[8], yp[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                xm[v] = bQi[(v * TI + tim) * 32 + lane];
+                ym[v] = __shfl_up_sync(0xffffffffu, qic[v], 1);
+            }
+            if (PATH == IMHD_PATH_B) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    xp[v] = bQi[(v * TI + tip) * 32 + lane];
+                    yp[v] = __shfl_down_sync(0xffffffffu, qic[v], 1);
+                }
+            }
+            if (PATH == IMHD_PATH_A) {
+                // FluidAdvanceLocalNoDiff: i,j,k >= 1 including the far faces (B-14)
+                if (k >= 1 && in_dom && !top && !left) corr_cell<PATH>(q0, qic, xm, ym, qim, xp, yp, qip, P, out);
+            } else {
+                if (k >= 1 && k <= P.Nz - 2) {
+                    if (interior_ij) corr_cell<PATH>(q0, qic, xm, ym, qim, xp, yp, qip, P, out);
+                } else if (k == 0) {
+                    if (interior_ij) {
+                        front_cell_exact(q0, qic, xm, ym, qim, xp, yp, qip, P, out);
+                    } else if (in_dom && (top || bottom)) {  // walls (0,j,0), (Nx-1,j,0): kernels_fluidbcs.cu:164-188
+                        out[RHO] = 1.0f;
+#pragma unroll
+                        for (int v = 1; v < 7; ++v) out[v] = 0.0f;
+                        float e = q0[EN];
+                        for (int rep = 0; rep < P.Nx; ++rep) {
+                            const float e2 = wall_e(e);
+                            if (e2 == e) break;
+                            e = e2;
+                        }
+                        out[EN] = e;
+                    }
+                } else if (bottom && right) {  // k == Nz-1: only the column (Nx-1,Ny-1) is "periodic" (B-8)
+                    out[RHO] = 1.0f;
+#pragma unroll
+                    for (int v = 1; v < 7; ++v) out[v] = 0.0f;
+                    out[EN] = A.corner_e;
+                }
+            }
+            // path A never computes plane 0: it is the copy of plane Nz-1 (PBCs), written below or by the exchange
+            if (owner && !(PATH == IMHD_PATH_A && k == 0)) {
+                const long long o = (long long)(k - A.kbase) * P.plane + lcol;
+#pragma unroll
+                for (int v = 0; v < 8; ++v) A.Qout[o + v * A.vs] = out[v];
+                // PBCs (kernels_fluidbcs.cu:498-510): Q[.,.,0] <- Q[.,.,Nz-1]; only when plane 0 is in this array
+                if (PATH == IMHD_PATH_A && k == P.Nz - 1 && A.k0 == 0) {
+                    const long long o0 = (long long)(0 - A.kbase) * P.plane + lcol;
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) A.Qout[o0 + v * A.vs] = out[v];
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            q0[v] = q1[v]; q1[v] = qn[v]; h1[v] = hn[v];
+            qim[v] = qic[v]; qic[v] = qip[v];
+        }
+    }
+}
+
+// Predictor plane k (global index, k <= Nz-2) into an (8,Nx,Ny) buffer: same device function, same
+// values as the fused kernel computes on chip.
+template <int PATH>
+__global__ void __launch_bounds__(256) k_qint_plane(const FusedArgs A, int k, float* __restrict__ out) {
+    const Params& P = A.P;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= P.Nx || j >= P.Ny) return;
+    const bool bottom = i == P.Nx - 1, right = j == P.Ny - 1;
+    const bool lap = PATH == IMHD_PATH_B && i > 0 && !bottom && j > 0 && !right && k >= 1;
+    auto off = [&](int ii, int jj, int kk) -> long long {
+        ii = min(max(ii, 0), P.Nx - 1); jj = min(max(jj, 0), P.Ny - 1); kk = min(max(kk, A.kmin), A.kmax);
+        return (long long)(kk - A.kbase) * P.plane + (long long)ii * P.Ny + jj;
+    };
+    float c[8], xp[8], yp[8], zp[8], xm[8], ym[8], zm[8], hc[8], hp[8], r[8];
+    ldg8(A.Qin, off(i, j, k), A.vs, c);
+    ldg8(A.Qin, off(i + 1, j, k), A.vs, xp);
+    ldg8(A.Qin, off(i, j + 1, k), A.vs, yp);
+    ldg8(A.Qin, off(i, j, k + 1), A.vs, zp);
+    ldg8(A.Qin, off(i - 1, j, k), A.vs, xm);
+    ldg8(A.Qin, off(i, j - 1, k), A.vs, ym);
+    ldg8(A.Qin, off(i, j, k - 1), A.vs, zm);
+    hflux(c, hc);
+    hflux(zp, hp);
+    qint_cell<PATH>(c, xp, yp, hc, hp, xm, ym, zm, zp, bottom, right, k == 0, lap, P, r);
+    const long long l = (long long)i * P.Ny + j;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) out[l + v * P.plane] = r[v];
+}
+
+}  // namespace imhd
+
+using namespace imhd;
+
+static int fill_args(FusedArgs& A, const float* Qin, float* Qout, const float* qlo, const float* qhi,
+                     const imhd_slab* s) {
+    if (!s) { set_error("null slab descriptor"); return IMHD_E_INVALID; }
+    if (int e = bad_dims(s->Nx, s->Ny, s->Nz)) return e;
+    if (s->path != IMHD_PATH_A && s->path != IMHD_PATH_B) { set_error("bad path %d", s->path); return IMHD_E_INVALID; }
+    if (s->k0 < 0 || s->nzl < 2 || s->k0 + s->nzl > s->Nz) {
+        set_error("bad slab: k0=%d nzl=%d Nz=%d (need nzl >= 2)", s->k0, s->nzl, s->Nz);
+        return IMHD_E_INVALID;
+    }
+    if (!s->ghosts && (s->k0 != 0 || s->nzl != s->Nz)) {
+        set_error("a slab that is not the whole domain needs ghosts=1");
+        return IMHD_E_INVALID;
+    }
+    A.P = make_params(s->path, s->D, s->dt, s->dx, s->dy, s->dz, s->Nx, s->Ny, s->Nz);
+    A.Qin = Qin; A.Qout = Qout;
+    const int g = s->ghosts ? 1 : 0;
+    A.vs = (long long)(s->nzl + 2 * g) * A.P.plane;
+    A.kbase = s->k0 - g;
+    A.kmin = max(s->k0 - g, 0);
+    A.kmax = min(s->k0 + s->nzl - 1 + g, s->Nz - 1);
+    A.k0 = s->k0; A.k1 = s->k0 + s->nzl;
+    A.qlo = qlo; A.qhi = qhi;
+    A.hi_plane = min(A.k1, s->Nz - 1);
+    A.corner_e = 0.0f;
+    return 0;
+}
+
+extern "C" int imhd_qint_plane(const float* Q, float* out_plane, int k, const imhd_slab* s, void* stream) {
+    FusedArgs A;
+    if (int e = fill_args(A, Q, nullptr, nullptr, nullptr, s)) return e;
+    if (k < 0 || k > s->Nz - 2 || k < A.kmin || k + 1 > A.kmax) {
+        set_error("imhd_qint_plane: plane %d not computable from array planes [%d,%d]", k, A.kmin, A.kmax);
+        return IMHD_E_INVALID;
+    }
+    const dim3 grid((s->Ny + 31) / 32, (s->Nx + 7) / 8), block(32, 8);
+    if (s->path == IMHD_PATH_A) k_qint_plane<IMHD_PATH_A><<<grid, block, 0, (cudaStream_t)stream>>>(A, k, out_plane);
+    else                        k_qint_plane<IMHD_PATH_B><<<grid, block, 0, (cudaStream_t)stream>>>(A, k, out_plane);
+    IMHD_LAUNCH_CHECK(1);
+    return 0;
+}
+
+extern "C" float imhd_wall_energy_fixed_point(float e, int max_iter) {
+    for (int rep = 0; rep < max_iter; ++rep) {  // kernels_fluidbcs.cu:173 (B-12), host copy of imhd::wall_e
+        const float p = (float)(kGm1 * ((e - 0.0f) - 0.0f / 2.0));
+        const float e2 = (float)(p / kGm1);
+        if (e2 == e) break;
+        e = e2;
+    }
+    return e;
+}
+
+template <int PATH, int TI>
+static int launch_fused(FusedArgs& A, cudaStream_t st) {
+    constexpr int O = Ring<PATH>::O;
+    constexpr int WI = TI - 2 * O, WJ = 32 - 2 * O;
+    const Params& P = A.P;
+    // cells needing a thread in the inner window: i in [1, Nx-1] (A) / [1, Nx-2] (B); edges ride along
+    const int ni = PATH == IMHD_PATH_A ? P.Nx - 1 : P.Nx - 2, nj = PATH == IMHD_PATH_A ? P.Ny - 1 : P.Ny - 2;
+    A.ntile_i = (ni + WI - 1) / WI;
+    A.ntile_j = (nj + WJ - 1) / WJ;
+    const int nzl = A.k1 - A.k0;
+    // chunk length: enough chunks for several waves of blocks, long enough to amortise the 2 warm-up planes
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (long long)A.ntile_i * A.ntile_j;
+    int nchunk = (int)((8LL * sms + tiles - 1) / tiles);
+    int chunk = (nzl + nchunk - 1) / nchunk;
+    if (chunk < 16) chunk = 16;
+    if (chunk > nzl) chunk = nzl;
+    if (A.chunk > 0) chunk = min(A.chunk, nzl);  // caller override (tests)
+    if (chunk < 2) chunk = 2;
+    A.chunk = chunk;
+    nchunk = (nzl + chunk - 1) / chunk;
+    // a trailing chunk of one plane would start its warm-up before the previous chunk's first plane: fine
+    const size_t smem = 2 * 2 * 8 * TI * 32 * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        IMHD_CUDA(cudaFuncSetAttribute(k_fused_step<PATH, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const dim3 grid(A.ntile_j, A.ntile_i, nchunk), block(32, TI);
+    k_fused_step<PATH, TI><<<grid, block, smem, st>>>(A);
+    IMHD_LAUNCH_CHECK(1);
+    return 0;
+}
+
+static int g_chunk_override = 0;
+extern "C" void imhd_set_chunk(int planes) { g_chunk_override = planes; }
+
+extern "C" int imhd_step_fused(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
+                               const imhd_slab* s, void* stream) {
+    FusedArgs A;
+    if (int e = fill_args(A, Qin, Qout, qint_lo, qint_hi, s)) return e;
+    if (Qin == Qout) { set_error("imhd_step_fused: Qin and Qout must be distinct buffers"); return IMHD_E_INVALID; }
+    if (!qint_hi || (s->path == IMHD_PATH_B && !qint_lo) || (s->k0 > 0 && !qint_lo)) {
+        set_error("imhd_step_fused: missing predictor ghost plane (qint_lo=%p qint_hi=%p)", (const void*)qint_lo, (const void*)qint_hi);
+        return IMHD_E_INVALID;
+    }
+    A.corner_e = s->corner_e;
+    A.chunk = g_chunk_override;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->path == IMHD_PATH_A) return launch_fused<IMHD_PATH_A, 16>(A, st);
+    return launch_fused<IMHD_PATH_B, 16>(A, st);
+}
+

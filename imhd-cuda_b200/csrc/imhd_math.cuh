@@ -1,0 +1,201 @@
+// Device math of the ideal-MHD Lax-Wendroff update: thermo helpers, the two flux families,
+// diffusion stencil.  Two arithmetic recipes, chosen by the template flag EXACT:
+//
+//   EXACT = true   mirrors the reference's fp32/fp64 rounding points operation by operation
+//                  (SURVEY.md A.6).  Used by the parity-granular operators (imhd_granular.cu,
+//                  compiled with -fmad=false) so they can be compared bit for bit.
+//   EXACT = false  the fast recipe of the fused kernels: fp32 flux evaluation with one
+//                  reciprocal per state, and the O(1) accumulations arranged so that the
+//                  last rounding is the only significant one (DESIGN.md "Precision").
+//
+// Reference formulas (file:line relative to the reference root):
+//   helpers          lib/on-device/helper_functions.cu:7-62
+//   indexed fluxes   lib/on-device/kernels_od_fluxes.cu:112-275  (predictor, BoundaryConditions)
+//   local fluxes     lib/on-device/kernels_od_fluxes.cu:8-104    (corrector)
+//   diffusion        lib/on-device/diffusion.cu:8-19
+// The live quirks of those formulas are reproduced on purpose.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace imhd {
+
+enum { RHO = 0, MX = 1, MY = 2, MZ = 3, BX = 4, BY = 5, BZ = 6, EN = 7 };
+enum { DIR_X = 0, DIR_Y = 1, DIR_Z = 2 };
+
+constexpr double kGamma = 5.0 / 3.0;  // include/on-device/kernels_od.cuh:16 (a double)
+constexpr double kGm1 = kGamma - 1.0;
+constexpr float kGm1f = (float)(kGamma - 1.0);
+
+__device__ __forceinline__ double sqd(float x) { return (double)x * (double)x; }  // pow(float,2)
+
+// ------------------------------------------------------------------------------------------
+// Derived quantities of one state (helper_functions.cu).
+// ------------------------------------------------------------------------------------------
+template <bool EXACT>
+struct Aux {
+    float Bsq, ke, p, Bdotu;
+    double inv;   // EXACT: 1.0/rho as the indexed family uses it
+    float invf;   // fast: fp32 reciprocal of rho
+};
+
+template <bool EXACT>
+__device__ __forceinline__ float h_Bsq(float bx, float by, float bz) {
+    if (EXACT) return (float)(sqd(bx) + sqd(by) + sqd(bz));
+    return fmaf(bz, bz, fmaf(by, by, bx * bx));
+}
+template <bool EXACT>
+__device__ __forceinline__ float h_KE(float rho, float mx, float my, float mz, float invf) {
+    if (EXACT) return (float)((1.0 / rho) * (sqd(mx) + sqd(my) + sqd(mz)));  // no 1/2 (B-1)
+    return invf * fmaf(mz, mz, fmaf(my, my, mx * mx));
+}
+template <bool EXACT>
+__device__ __forceinline__ float h_p(float e, float Bsq, float ke) {
+    if (EXACT) return (float)(kGm1 * ((e - ke) - Bsq / 2.0));
+    return kGm1f * fmaf(-0.5f, Bsq, e - ke);
+}
+template <bool EXACT>
+__device__ __forceinline__ float h_Bdotu(float rho, float mx, float my, float mz, float bx, float by,
+                                         float bz, float invf) {
+    if (EXACT) return (float)((1.0 / rho) * (mx * bx + my * by + mz * bz));
+    return invf * fmaf(mz, bz, fmaf(my, by, mx * bx));
+}
+
+__device__ __forceinline__ float fast_rcp(float x) {
+    // one Newton step on the hardware approximation: <= 1 ulp, no denormal/inf special cases
+    // needed (rho is O(0.01..1)).
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+
+template <bool EXACT>
+__device__ __forceinline__ Aux<EXACT> make_aux(const float U[8]) {
+    Aux<EXACT> a;
+    a.inv = EXACT ? 1.0 / U[RHO] : 0.0;
+    a.invf = EXACT ? 0.0f : fast_rcp(U[RHO]);
+    a.Bsq = h_Bsq<EXACT>(U[BX], U[BY], U[BZ]);
+    a.ke = h_KE<EXACT>(U[RHO], U[MX], U[MY], U[MZ], a.invf);
+    a.p = h_p<EXACT>(U[EN], a.Bsq, a.ke);
+    a.Bdotu = h_Bdotu<EXACT>(U[RHO], U[MX], U[MY], U[MZ], U[BX], U[BY], U[BZ], a.invf);
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------
+// INDEXED flux family (kernels_od_fluxes.cu:112-275): d-direction flux of all 8 variables of
+// state U.  c = component index of the direction (MX+d, BX+d).
+// ------------------------------------------------------------------------------------------
+template <bool EXACT, int DIR>
+__device__ __forceinline__ void flux_indexed(const float U[8], const Aux<EXACT>& a, float f[8]) {
+    const float rho = U[RHO];
+    const float md = U[MX + DIR], bd = U[BX + DIR];
+    f[RHO] = md;  // :112-126
+    if (EXACT) {
+        const double inv = a.inv;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float mc = U[MX + c], bc = U[BX + c];
+            if (c == DIR) {
+                // :129-137,159-167,184-192   (1/rho)*m^2 - B^2 + p + Bsq/2
+                f[MX + c] = (float)(inv * sqd(md) - sqd(bd) + a.p + a.Bsq / 2.0);
+                f[BX + c] = 0.0f;  // :195,217,237
+            } else {
+                // :138-149,168-173 and their aliases :152-183: (1/rho)*m_lo*m_hi - B_lo*B_hi with
+                // lo < hi component order (x before y before z), the product order of the source
+                const int lo = c < DIR ? c : DIR, hi = c < DIR ? DIR : c;
+                f[MX + c] = (float)(inv * U[MX + lo] * U[MX + hi] - U[BX + lo] * U[BX + hi]);
+                // induction (B-2): the primary definitions are YFluxBX, ZFluxBX, ZFluxBY
+                //   G(Bx) = (1/rho) mx By - Bx my ; H(Bx) = (1/rho) mx Bz - Bx mz ;
+                //   H(By) = (1/rho) my Bz - By mz ; the transposed ones are -1.0 * those.
+                if (c < DIR) f[BX + c] = (float)(inv * mc * bd - bc * md);
+                else         f[BX + c] = (float)(-1.0 * (float)(inv * md * bc - bd * mc));
+            }
+        }
+        // :243-275 all fp32 (B-3): e + p + Bsq*(m_d/rho) - Bdotu*B_d
+        f[EN] = U[EN] + a.p + a.Bsq * (md / rho) - a.Bdotu * bd;
+    } else {
+        const float inv = a.invf;
+        const float ud = md * inv;
+        const float ptot = fmaf(0.5f, a.Bsq, a.p);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float mc = U[MX + c], bc = U[BX + c];
+            if (c == DIR) {
+                f[MX + c] = fmaf(ud, md, fmaf(-bd, bd, ptot));
+                f[BX + c] = 0.0f;
+            } else {
+                f[MX + c] = fmaf(ud, mc, -(bc * bd));
+                if (c < DIR) f[BX + c] = fmaf(inv * mc, bd, -(bc * md));
+                else         f[BX + c] = -fmaf(ud, bc, -(bd * mc));
+            }
+        }
+        f[EN] = fmaf(-a.Bdotu, bd, fmaf(a.Bsq, ud, U[EN] + a.p));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// LOCAL flux family (kernels_od_fluxes.cu:8-104): d-direction flux of state U with
+// EXPLICIT p, Bsq, Bdotu (the corrector feeds mixed-neighbour values at k-1: B-4, B-5).
+// ------------------------------------------------------------------------------------------
+template <bool EXACT, int DIR>
+__device__ __forceinline__ void flux_local(const float U[8], float p, float Bsq, float Bdotu, float invf,
+                                           float f[8]) {
+    const float rho = U[RHO];
+    const float md = U[MX + DIR], bd = U[BX + DIR];
+    f[RHO] = md;
+    if (EXACT) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float mc = U[MX + c], bc = U[BX + c];
+            if (c == DIR) {
+                f[MX + c] = (float)(sqd(md) / rho - sqd(bd) + p + 0.5 * Bsq);  // :12-14,49-51,82-84
+                f[BX + c] = 0.0f;
+            } else {
+                f[MX + c] = (mc * md) / rho - bc * bd;              // fp32 (:16-22,45-47,53-55,78-80...)
+                f[BX + c] = (mc / rho) * bd - (md / rho) * bc;      // fp32 (:28-34,57-67,90-96)
+            }
+        }
+        f[EN] = (float)((U[EN] + p + 0.5 * Bsq) * (md / rho) - Bdotu * bd);  // :36-38,69-71,102-104
+    } else {
+        const float ud = md * invf;
+        const float ptot = fmaf(0.5f, Bsq, p);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float mc = U[MX + c], bc = U[BX + c];
+            if (c == DIR) {
+                f[MX + c] = fmaf(ud, md, fmaf(-bd, bd, ptot));
+                f[BX + c] = 0.0f;
+            } else {
+                f[MX + c] = fmaf(ud, mc, -(bc * bd));
+                f[BX + c] = fmaf(mc * invf, bd, -(ud * bc));
+            }
+        }
+        f[EN] = fmaf(U[EN] + ptot, ud, -(Bdotu * bd));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Diffusion stencil D * lap(q) (diffusion.cu:8-19); cx = 1/dx^2 etc. precomputed in fp64 on the
+// host exactly as `1.0 / pow(dx, 2)`.
+// ------------------------------------------------------------------------------------------
+struct DiffCoef {
+    double cx, cy, cz;     // EXACT
+    float cxf, cyf, czf;   // fast
+};
+
+template <bool EXACT>
+__device__ __forceinline__ float num_diff(float q, float qip1, float qjp1, float qkp1, float qim1, float qjm1,
+                                          float qkm1, float D, const DiffCoef& c) {
+    if (EXACT)
+        return (float)(D * (c.cx * (qip1 - 2.0 * q + qim1) + c.cy * (qjp1 - 2.0 * q + qjm1) +
+                            c.cz * (qkp1 - 2.0 * q + qkm1)));
+    const float m2q = -2.0f * q;
+    return D * fmaf(c.czf, (qkp1 + m2q) + qkm1, fmaf(c.cyf, (qjp1 + m2q) + qjm1, c.cxf * ((qip1 + m2q) + qim1)));
+}
+
+// wall energy e <- p(e,0,0)/(gamma-1): kernels_fluidbcs.cu:173,451,461 (B-12)
+__device__ __forceinline__ float wall_e(float e) {
+    float p = (float)(kGm1 * ((e - 0.0f) - 0.0f / 2.0));
+    return (float)(p / kGm1);
+}
+
+}  // namespace imhd

@@ -1,0 +1,212 @@
+"""Operator-level Python surface over the C ABI.
+
+Two layers, both thin:
+
+* free functions over torch CUDA tensors (``predictor``, ``corrector``, ``fluid_bcs``, ``step_fused`` ...):
+  PyTorch supplies device memory and the current stream, the library does all the work.  They mirror
+  the reference's kernel groups (argument order of include/on-device/*.cuh: state arrays, then
+  ``D, dt, dx, dy, dz``; the grid size is taken from the tensor shape ``(8, Nz, Nx, Ny)``).
+* ``Context`` -- the ``imhd_ctx`` the drop-in drivers use (host numpy in / out).
+
+Nothing here computes: a missing or unloadable ``libimhd_b200.so`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import PATH_A, PATH_B, Slab, check
+
+VARS = ("rho", "rhovx", "rhovy", "rhovz", "Bx", "By", "Bz", "e")
+
+
+def _stream():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(t, shape=None):
+    import torch
+
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise TypeError("expected a contiguous float32 CUDA tensor")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    return C.c_void_p(t.data_ptr())
+
+
+def _dims(Q):
+    if Q.dim() != 4 or Q.shape[0] != 8:
+        raise ValueError("state tensors have shape (8, Nz, Nx, Ny)")
+    _, Nz, Nx, Ny = Q.shape
+    return Nx, Ny, Nz
+
+
+def grid_spacing(lo: float, hi: float, n: int) -> float:
+    """fp32 ``(hi - lo) / (n - 1)`` as the reference drivers compute dx (main.cu:98-100)."""
+    return float(np.float32((np.float32(hi) - np.float32(lo)) / np.float32(n - 1)))
+
+
+# ---- parity-granular operators ------------------------------------------------------------------
+def predictor(Q, Qint, path, D, dt, dx, dy, dz):
+    L = _lib.load()
+    check(L.imhd_predictor(_dev(Q), _dev(Qint, Q.shape), path, D, dt, dx, dy, dz, *_dims(Q), _stream()))
+
+
+def corrector(Q, Qint, path, D, dt, dx, dy, dz):
+    L = _lib.load()
+    check(L.imhd_corrector(_dev(Q), _dev(Qint, Q.shape), path, D, dt, dx, dy, dz, *_dims(Q), _stream()))
+
+
+def fluid_bcs(Q, Qint, path, D, dt, dx, dy, dz):
+    L = _lib.load()
+    check(L.imhd_fluid_bcs(_dev(Q), _dev(Qint, Q.shape), path, D, dt, dx, dy, dz, *_dims(Q), _stream()))
+
+
+def initial_bcs(Q):
+    L = _lib.load()
+    check(L.imhd_initial_bcs(_dev(Q), *_dims(Q), _stream()))
+
+
+def init_grids(bounds, Nx, Ny, Nz, device="cuda"):
+    import torch
+
+    L = _lib.load()
+    x, y, z = (torch.empty(n, dtype=torch.float32, device=device) for n in (Nx, Ny, Nz))
+    check(L.imhd_init_grids(_dev(x), _dev(y), _dev(z), *[float(b) for b in bounds], Nx, Ny, Nz, _stream()))
+    return x, y, z
+
+
+def init_screwpinch_stride(J0, x, y, z):
+    import torch
+
+    L = _lib.load()
+    Q = torch.empty((8, len(z), len(x), len(y)), dtype=torch.float32, device=x.device)
+    check(L.imhd_init_screwpinch_stride(_dev(Q), J0, _dev(x), _dev(y), _dev(z), len(x), len(y), len(z), _stream()))
+    return Q
+
+
+def init_cubic_bennett_vortex_m0(k, A, x, y, z):
+    import torch
+
+    L = _lib.load()
+    Q = torch.empty((8, len(z), len(x), len(y)), dtype=torch.float32, device=x.device)
+    check(L.imhd_init_cubic_bennett_vortex_m0(_dev(Q), k, A, _dev(x), _dev(y), _dev(z), len(x), len(y), len(z),
+                                              _stream()))
+    return Q
+
+
+# ---- fused step -----------------------------------------------------------------------------------
+def make_slab(Nx, Ny, Nz, path, D, dt, dx, dy, dz, k0=0, nzl=None, ghosts=0, corner_e=0.0) -> Slab:
+    return Slab(Nx, Ny, Nz, k0, Nz if nzl is None else nzl, ghosts, path, D, dt, dx, dy, dz, corner_e)
+
+
+def qint_plane(Q, k, slab: Slab, out=None):
+    """Predictor plane Qint(.,.,k) (global k) from a slab array -> (8, Nx, Ny)."""
+    import torch
+
+    L = _lib.load()
+    if out is None:
+        out = torch.empty((8, slab.Nx, slab.Ny), dtype=torch.float32, device=Q.device)
+    check(L.imhd_qint_plane(_dev(Q), _dev(out, (8, slab.Nx, slab.Ny)), k, C.byref(slab), _stream()))
+    return out
+
+
+def step_fused(Qin, Qout, qint_lo, qint_hi, slab: Slab):
+    L = _lib.load()
+    lo = _dev(qint_lo) if qint_lo is not None else None
+    check(L.imhd_step_fused(_dev(Qin), _dev(Qout, Qin.shape), lo, _dev(qint_hi), C.byref(slab), _stream()))
+
+
+def wall_energy_fixed_point(e: float, max_iter: int) -> float:
+    return float(_lib.load().imhd_wall_energy_fixed_point(e, max_iter))
+
+
+def step_full_domain(Qin, Qout, path, D, dt, dx, dy, dz, corner_e=0.0):
+    """One fused step of a whole-domain (8,Nz,Nx,Ny) array on one GPU, including the periodic wrap planes."""
+    Nx, Ny, Nz = _dims(Qin)
+    s = make_slab(Nx, Ny, Nz, path, D, dt, dx, dy, dz, corner_e=corner_e)
+    lo = qint_plane(Qin, Nz - 2, s)
+    hi = qint_plane(Qin, 0, s)
+    step_fused(Qin, Qout, lo, hi, s)
+
+
+def launch_count() -> int:
+    return int(_lib.load().imhd_launch_count())
+
+
+# ---- context ------------------------------------------------------------------------------------------
+class Context:
+    """``imhd_ctx``: what src/on-device/main.cu / no_diffusion.cu own between their IC and their time loop."""
+
+    def __init__(self, Nx: int, Ny: int, Nz: int, device: int = 0):
+        self.L = _lib.load()
+        self.Nx, self.Ny, self.Nz = Nx, Ny, Nz
+        self.h = self.L.imhd_create(Nx, Ny, Nz, device)
+        if not self.h:
+            raise _lib.ImhdError(-1, self.L.imhd_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.imhd_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def shape(self):
+        return (8, self.Nz, self.Nx, self.Ny)
+
+    def init_grids(self, x_min, x_max, y_min, y_max, z_min, z_max):
+        check(self.L.imhd_ctx_init_grids(self.h, x_min, x_max, y_min, y_max, z_min, z_max))
+
+    def init_screwpinch_stride(self, J0):
+        check(self.L.imhd_ctx_init_screwpinch_stride(self.h, J0))
+
+    def init_cubic_bennett_vortex_m0(self, k, A):
+        check(self.L.imhd_ctx_init_cubic_bennett_vortex_m0(self.h, k, A))
+
+    def set_state(self, Q: np.ndarray):
+        Q = np.ascontiguousarray(Q, dtype=np.float32)
+        assert Q.shape == self.shape
+        check(self.L.imhd_ctx_set_state(self.h, Q.ctypes.data_as(C.c_void_p)))
+        check(self.L.imhd_ctx_synchronize(self.h))  # Q may be a temporary
+
+    def set_spacing(self, dx, dy, dz):
+        check(self.L.imhd_ctx_set_spacing(self.h, dx, dy, dz))
+
+    def prime(self, path, D, dt):
+        check(self.L.imhd_ctx_prime(self.h, path, D, dt))
+
+    def step(self, nsteps=1):
+        check(self.L.imhd_ctx_step(self.h, nsteps))
+
+    def step_granular(self, nsteps=1):
+        check(self.L.imhd_ctx_step_granular(self.h, nsteps))
+
+    def synchronize(self):
+        check(self.L.imhd_ctx_synchronize(self.h))
+
+    def get_state(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.shape, np.float32)
+        check(self.L.imhd_ctx_get_state(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def get_grids(self):
+        x, y, z = (np.empty(n, np.float32) for n in (self.Nx, self.Ny, self.Nz))
+        check(self.L.imhd_ctx_get_grids(self.h, *(a.ctypes.data_as(C.c_void_p) for a in (x, y, z))))
+        return x, y, z
+
+    def run_host(self, Q_in: np.ndarray, Q_out: np.ndarray, path, D, dt, dx, dy, dz, nsteps):
+        check(self.L.imhd_run_host(self.h, Q_in.ctypes.data_as(C.c_void_p), Q_out.ctypes.data_as(C.c_void_p), path, D,
+                                   dt, dx, dy, dz, nsteps))

@@ -1,0 +1,169 @@
+/*
+ * imhd_b200.h -- C ABI of libimhd_b200.so, the B200-native (sm_100a) replacement for the
+ * Lax-Wendroff hot path of russellmatt66/imhd-CUDA.
+ *
+ * The reference has no C ABI: its "operator API" is the set of C++-mangled __global__ kernels
+ * declared in include/on-device/{kernels_od,kernels_fluidbcs,kernels_od_intvar,kernels_intvarbcs,
+ * initialize_od}.cuh, launched by src/on-device/main.cu (Path B, with diffusion) and
+ * src/on-device/no_diffusion.cu (Path A).  Each entry point below names the reference
+ * interface it replaces (file:line, relative to the reference root).  INTEGRATION.md shows the
+ * binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  `stream` is a cudaStream_t passed as void* (NULL = legacy
+ *    default stream).  Everything is stream-ordered; nothing synchronises the device unless
+ *    stated.  One host thread per context.
+ *  - Every function returns 0 on success or a non-zero code (a cudaError_t, or IMHD_E_*);
+ *    imhd_last_error() describes the last failure on the calling thread.  Nothing throws or
+ *    calls exit() (the reference's checkCuda aborts: include/on-device/utils/utils.cuh:8-16).
+ *  - State arrays are fp32 in the reference's IDX3D layout (lib/on-device/kernels_od.cu:11,16):
+ *        l = k*Nx*Ny + i*Ny + j,  variable v at l + v*Nx*Ny*Nz,
+ *        v = rho, rhovx, rhovy, rhovz, Bx, By, Bz, e          (j is unit stride)
+ *    with 64-bit offsets inside (the reference's int offsets overflow above 306 M cells).
+ *  - `path`: IMHD_PATH_A = no_diffusion.cu pipeline, IMHD_PATH_B = main.cu pipeline (D used).
+ *  - There is NO CPU fallback: every compute entry point launches sm_100a kernels and fails
+ *    with the CUDA error if no device is usable.
+ */
+#ifndef IMHD_B200_H
+#define IMHD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMHD_PATH_A 0 /* src/on-device/no_diffusion.cu:284-312 */
+#define IMHD_PATH_B 1 /* src/on-device/main.cu:196-213        */
+
+#define IMHD_E_INVALID 10001 /* bad argument                     */
+#define IMHD_E_STATE 10002   /* call order / context state error */
+#define IMHD_E_IO 10003      /* file output failed               */
+
+/* Bit flags for imhd_set_options(): which arithmetic the fused kernels use. */
+#define IMHD_OPT_DEFAULT 0u
+
+typedef struct imhd_ctx imhd_ctx;
+
+/* ---- library ------------------------------------------------------------------------- */
+int imhd_abi_version(void);
+const char* imhd_last_error(void);
+/* Number of kernels this library has launched on the calling process since load (bench.py's
+ * gpu_launches claim is read from here, not estimated). */
+uint64_t imhd_launch_count(void);
+
+/* ---- parity-granular operators on caller-owned DEVICE buffers (full domain, IDX3D) -------
+ * These mirror the reference kernels one group at a time and keep its fp32/fp64 rounding
+ * points (compiled without FMA contraction), so they can be compared call by call. */
+
+/* Predictor: every cell of Qint, exactly as the reference's kernel sequence leaves it.
+ *  A: ComputeIntermediateVariablesNoDiff (lib/on-device/kernels_od_intvar.cu:51) +
+ *     QintBdry{Front,LeftRight,TopBottom,FrontBottom,FrontRight,BottomRight}NoDiff + QintBdryPBCs
+ *     (lib/on-device/kernels_intvarbcs.cu:360-558)
+ *  B: ComputeIntermediateVariablesStride (kernels_od_intvar.cu:113) +
+ *     ComputeIntermediateVariablesBoundary (kernels_intvarbcs.cu:177) */
+int imhd_predictor(const float* Q, float* Qint, int path, float D, float dt, float dx, float dy,
+                   float dz, int Nx, int Ny, int Nz, void* stream);
+
+/* Corrector over the volume, in place.
+ *  A: FluidAdvanceLocalNoDiff (lib/on-device/kernels_od.cu:353)   B: FluidAdvanceLocal (:82) */
+int imhd_corrector(float* Q, const float* Qint, int path, float D, float dt, float dx, float dy,
+                   float dz, int Nx, int Ny, int Nz, void* stream);
+
+/* Fluid boundary pass that follows the corrector each step.
+ *  A: PBCs (lib/on-device/kernels_fluidbcs.cu:498)
+ *  B: BoundaryConditions (kernels_fluidbcs.cu:32), single-application semantics */
+int imhd_fluid_bcs(float* Q, const float* Qint, int path, float D, float dt, float dx, float dy,
+                   float dz, int Nx, int Ny, int Nz, void* stream);
+
+/* Path A initial boundary pass: rigidConductingWallBCsLeftRight + (no-op) ...TopBottom + PBCs
+ * (kernels_fluidbcs.cu:436,467,498; call site no_diffusion.cu:174-177). */
+int imhd_initial_bcs(float* Q, int Nx, int Ny, int Nz, void* stream);
+
+/* ---- grids and initial conditions (lib/on-device/initialize_od.cu) ------------------------ */
+/* InitializeX/Y/Z (:26-57) with dx = (x_max-x_min)/(Nx-1) in fp32 (main.cu:98-100). */
+int imhd_init_grids(float* x, float* y, float* z, float x_min, float x_max, float y_min,
+                    float y_max, float z_min, float z_max, int Nx, int Ny, int Nz, void* stream);
+/* ScrewPinchStride (:269-345) */
+int imhd_init_screwpinch_stride(float* Q, float J0, const float* x, const float* y, const float* z,
+                                int Nx, int Ny, int Nz, void* stream);
+/* CubicBennettVortex_m0 (:132-205); `k` is accepted and, as in the reference, shadowed by the
+ * z loop index. */
+int imhd_init_cubic_bennett_vortex_m0(float* Q, float k, float A, const float* x, const float* y,
+                                      const float* z, int Nx, int Ny, int Nz, void* stream);
+
+/* ---- fused time step: the product hot path ---------------------------------------------------
+ * One sweep Q^n -> Q^{n+1}: predictor, corrector, diffusion and every boundary pass of one
+ * reference time step (main.cu:200-213 / no_diffusion.cu:288-311), with Qint living only
+ * on chip.  Qin and Qout are distinct device buffers (ping-pong); the reference's `intvars`
+ * allocation becomes the second buffer.
+ *
+ * Slab form (z-slab domain decomposition, one slab per GPU): the buffers hold global planes
+ * [k0-1, k0+nzl] -- nzl owned planes plus one ghost plane on each side -- as a
+ * (8, nzl+2, Nx, Ny) array; pass k0 = 0, nzl = Nz and ghosts = 0 for a plain (8,Nz,Nx,Ny)
+ * full-domain array.  qint_lo / qint_hi are the (8,Nx,Ny) predictor planes just below and
+ * just above the slab (periodic in z with period Nz-1), produced by imhd_qint_plane on the
+ * neighbouring rank (or on this one when the slab touches both ends). */
+typedef struct {
+    int Nx, Ny, Nz;     /* global grid                                        */
+    int k0, nzl;        /* first owned global plane, number of owned planes   */
+    int ghosts;         /* 0: no ghost planes in the arrays, 1: one each side */
+    int path;           /* IMHD_PATH_A / IMHD_PATH_B                           */
+    float D, dt, dx, dy, dz;
+    float corner_e;     /* path B only: imhd_wall_energy_fixed_point(e of Q(Nx-1,Ny-1,0) at t=0);
+                           the value BoundaryConditions leaves in the column (Nx-1,Ny-1) at k=0
+                           and k=Nz-1 (lib/on-device/kernels_fluidbcs.cu:178-188,227-231) */
+} imhd_slab;
+
+int imhd_step_fused(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
+                    const imhd_slab* s, void* stream);
+
+/* e <- p(e,0,0)/(gamma-1) iterated to its fixed point (lib/on-device/kernels_fluidbcs.cu:173,187; every
+ * x-thread of the reference launch re-applies it).  Scalar host helper, identity when e == 0. */
+float imhd_wall_energy_fixed_point(float e, int max_iter);
+
+/* Test hook: force the z-chunk length of the fused kernel (0 = automatic). */
+void imhd_set_chunk(int planes);
+
+/* Predictor plane Qint(.,.,k) for one owned global plane k into an (8,Nx,Ny) device buffer
+ * (the data a neighbouring slab needs as qint_lo / qint_hi). */
+int imhd_qint_plane(const float* Q, float* out_plane, int k, const imhd_slab* s, void* stream);
+
+/* ---- context API: what the drop-in drivers (imhd-cuda, imhd-cuda_nodiff) call ------------------
+ * Owns the ping-pong state buffers, grids and staging for one GPU (one slab). */
+imhd_ctx* imhd_create(int Nx, int Ny, int Nz, int device);
+void imhd_destroy(imhd_ctx* ctx);
+/* x_min..z_max as argv 8-13 (A) / 7-12 (B) of the reference drivers. */
+int imhd_ctx_init_grids(imhd_ctx* ctx, float x_min, float x_max, float y_min, float y_max,
+                        float z_min, float z_max);
+int imhd_ctx_init_screwpinch_stride(imhd_ctx* ctx, float J0);
+int imhd_ctx_init_cubic_bennett_vortex_m0(imhd_ctx* ctx, float k, float A);
+/* Upload a host state (8*Nx*Ny*Nz floats, IDX3D) instead of running an IC kernel. */
+int imhd_ctx_set_state(imhd_ctx* ctx, const float* host_Q);
+/* Grid spacing for a state uploaded with imhd_ctx_set_state (imhd_ctx_init_grids sets it too). */
+int imhd_ctx_set_spacing(imhd_ctx* ctx, float dx, float dy, float dz);
+/* Everything the reference drivers do between the IC kernel and the time loop
+ * (no_diffusion.cu:174-199 / main.cu:108-112). */
+int imhd_ctx_prime(imhd_ctx* ctx, int path, float D, float dt);
+/* nsteps iterations of the time loop, fused kernels, no host sync. */
+int imhd_ctx_step(imhd_ctx* ctx, int nsteps);
+/* Same, through the parity-granular operators (4 reference-shaped passes per step). */
+int imhd_ctx_step_granular(imhd_ctx* ctx, int nsteps);
+/* Copy the current state / intermediate state / grids to host memory (synchronises). */
+int imhd_ctx_get_state(imhd_ctx* ctx, float* host_Q);
+int imhd_ctx_get_grids(imhd_ctx* ctx, float* x, float* y, float* z);
+/* Device pointer of the current state (valid until the next step call). */
+float* imhd_ctx_device_state(imhd_ctx* ctx);
+void* imhd_ctx_stream(imhd_ctx* ctx);
+int imhd_ctx_synchronize(imhd_ctx* ctx);
+
+/* Whole job through HOST buffers (the e2e path bench.py times): upload host_Q_in, prime,
+ * run nsteps fused steps, download into host_Q_out.  Both buffers 8*Nx*Ny*Nz floats. */
+int imhd_run_host(imhd_ctx* ctx, const float* host_Q_in, float* host_Q_out, int path, float D,
+                  float dt, float dx, float dy, float dz, int nsteps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMHD_B200_H */

@@ -1,0 +1,57 @@
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def imhd():
+    """The product package (hyphenated directory name -> importlib)."""
+    return importlib.import_module("imhd-cuda_b200")
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    from oracle import oracle as o
+
+    if not os.path.exists(os.path.join(ROOT, "oracle", "libimhd_oracle.so")):
+        o.build()
+    return o
+
+
+@pytest.fixture(scope="session")
+def O(oracle_mod):
+    return oracle_mod.Oracle()
+
+
+@pytest.fixture(scope="session")
+def R(oracle_mod):
+    try:
+        return oracle_mod.Reference()
+    except (FileNotFoundError, OSError):
+        pytest.skip("oracle/_ref/libimhd_ref_cpu.so not built (needs /root/reference)")
+
+
+BOUNDS = (-3.14159, 3.14159) * 3  # build/on-device/input.inp:8-13
+
+
+def make_case(O, oracle_mod, Nx, Ny, Nz, ic="screwpinch"):
+    """Grids, spacings and initial state of a synthetic case, from the CPU oracle."""
+    g = O.init_grids(BOUNDS, Nx, Ny, Nz)
+    d = tuple(float(oracle_mod.grid_spacing(BOUNDS[2 * a], BOUNDS[2 * a + 1], n)) for a, n in enumerate((Nx, Ny, Nz)))
+    Q = O.screwpinch_stride(1.0, *g) if ic == "screwpinch" else O.cubic_bennett_vortex_m0(2.0, 0.5, *g)
+    return g, d, Q
+
+
+def bits_equal(a: np.ndarray, b: np.ndarray) -> bool:
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
