@@ -198,10 +198,13 @@ extern "C" int imhd_ctx_step(imhd_ctx* c, int nsteps) {
     for (int st = 0; st < nsteps; ++st) {
         const float* Qin = c->buf[c->cur];
         float* Qout = c->buf[1 - c->cur];
-        // periodic wrap: Qint(-1) == Qint(Nz-2) and Qint(Nz-1) == Qint(0)
-        if (int e = imhd_qint_plane(Qin, c->qint_planes, c->Nz - 2, &s, c->stream)) return e;
-        if (int e = imhd_qint_plane(Qin, c->qint_planes + pl8, 0, &s, c->stream)) return e;
-        if (int e = imhd_step_fused(Qin, Qout, c->qint_planes, c->qint_planes + pl8, &s, c->stream)) return e;
+        // periodic wrap: Qint(Nz-1) == Qint(0) and Qint(-1) == Qint(Nz-2)
+        float* q0 = c->qint_planes;
+        float* qw = c->qint_planes + pl8;
+        if (int e = imhd_qint_plane(Qin, q0, 0, &s, c->stream)) return e;
+        if (c->path == IMHD_PATH_B)
+            if (int e = imhd_qint_plane(Qin, qw, c->Nz - 2, &s, c->stream)) return e;
+        if (int e = imhd_step_fused(Qin, Qout, q0, q0, qw, &s, c->stream)) return e;
         c->cur = 1 - c->cur;
     }
     c->qint_valid = false;

@@ -17,6 +17,10 @@
 //   - z is cut into chunks for load balance; a chunk re-derives Qint(ka-1), Qint(ka) in two
 //     warm-up planes.  At slab ends the predictor plane just outside the slab comes from the
 //     qint_lo / qint_hi buffers (periodic wrap on one GPU, neighbour rank on several).
+//   - the two planes with their own rules stay OUT of the marching loop (they are 2 of Nz planes and
+//     would drag divergent, register-hungry code through every iteration): plane 0 (path A: periodic
+//     copy of plane Nz-1; path B: the BoundaryConditions face) and, for path B, plane Nz-1 (carried
+//     over except one column) are written by the small plane kernels below.
 //
 // Arithmetic: the "fast" recipe of imhd_math.cuh (fp32 fluxes, one reciprocal per state), with the
 // O(1) sums arranged to round where the reference rounds (DESIGN.md "Precision").  The k=0 face of
@@ -35,8 +39,10 @@ struct FusedArgs {
     int kbase;          // global plane index held by array plane 0
     int kmin, kmax;     // global planes that may be READ from Qin: [kmin, kmax]
     int k0, k1;         // owned (written) global planes [k0, k1)
-    const float* qlo;   // (8,Nx,Ny) Qint at global plane lo_plane (k0-1; Nz-2 data when k0 == 0)
+    int ka0, kb0;       // planes the marching kernel writes: [max(k0,1), min(k1, A: Nz / B: Nz-1))
+    const float* qlo;   // (8,Nx,Ny) Qint at global plane ka0-1  (own Qint(0) when k0 == 0)
     const float* qhi;   // (8,Nx,Ny) Qint at global plane hi_plane = min(k1, Nz-1)
+    const float* qwrap; // (8,Nx,Ny) Qint(Nz-2) == Qint(-1): path B, slab with k0 == 0 only (k=0 face)
     int hi_plane;
     int chunk;          // owned planes per z-chunk
     int ntile_i, ntile_j;
@@ -137,7 +143,7 @@ __device__ __forceinline__ void corr_cell(const float q[8], const float c[8], co
 
 // Path B, k = 0 face (BoundaryConditions, kernels_fluidbcs.cu:52-116): corrector with INDEXED fluxes of
 // Qint, k-1 -> Nz-2, + dt*numericalDiffusionFront; exact recipe (1 plane in Nz, not worth a fast one).
-__device__ __noinline__ void front_cell_exact(const float q[8], const float c[8], const float xm[8], const float ym[8],
+__device__ __forceinline__ void front_cell_exact(const float q[8], const float c[8], const float xm[8], const float ym[8],
                                               const float zm[8], const float xp[8], const float yp[8],
                                               const float zp[8], const Params& P, float out[8]) {
     float f[8], g[8], h[8], t[8], dF[8], dG[8], dH[8];
@@ -163,10 +169,10 @@ __device__ __noinline__ void front_cell_exact(const float q[8], const float c[8]
 }
 
 // -----------------------------------------------------------------------------------------------
-// The fused z-marching kernel.
+// The fused z-marching kernel: planes [ka0, kb0) of the slab.
 // -----------------------------------------------------------------------------------------------
 template <int PATH, int TI>
-__global__ void __launch_bounds__(TI * 32) k_fused_step(const FusedArgs A) {
+__global__ void __launch_bounds__(TI * 32, 1) k_fused_step(const FusedArgs A) {
     constexpr int O = Ring<PATH>::O;
     constexpr int WI = TI - 2 * O, WJ = 32 - 2 * O;
     extern __shared__ float smem[];
@@ -183,127 +189,89 @@ __global__ void __launch_bounds__(TI * 32) k_fused_step(const FusedArgs A) {
     const long long lcol = (long long)ic * P.Ny + jc;
     const bool top = (i == 0), bottom = (i == P.Nx - 1), left = (j == 0), right = (j == P.Ny - 1);
     const bool interior_ij = in_dom && !top && !bottom && !left && !right;
+    // cells the corrector updates in this path (k range is handled by the loop bounds)
+    const bool upd = PATH == IMHD_PATH_A ? (in_dom && !top && !left) : interior_ij;
     // cells this thread writes: the tile's inner window, widened to the domain edge on edge tiles
     const int oi_lo = bi == 0 ? 0 : 1 + bi * WI, oi_hi = bi == A.ntile_i - 1 ? P.Nx : 1 + (bi + 1) * WI;
     const int oj_lo = bj == 0 ? 0 : 1 + bj * WJ, oj_hi = bj == A.ntile_j - 1 ? P.Ny : 1 + (bj + 1) * WJ;
     const bool owner = in_dom && i >= oi_lo && i < oi_hi && j >= oj_lo && j < oj_hi;
-    // shared-memory slots of this thread and of its i-1 / i+1 rows
     const int tim = max(ti - 1, 0), tip = min(ti + 1, TI - 1);
+    const int so = ti * 32 + lane, som = tim * 32 + lane, sop = tip * 32 + lane;  // smem slots: own, i-1, i+1
 
-    const int ka = A.k0 + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.k1);
+    const int ka = A.ka0 + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kb0);
     const bool first = blockIdx.z == 0;
     const int ks = first ? ka - 1 : ka - 2;
 
-    auto plane_off = [&](int k) -> long long {
+    auto plane_ptr = [&](int k) -> const float* {
         const int kc = min(max(k, A.kmin), A.kmax);
-        return (long long)(kc - A.kbase) * P.plane + lcol;
+        return A.Qin + (long long)(kc - A.kbase) * P.plane + lcol;
     };
 
     float q0[8], q1[8], h1[8], qim[8], qic[8];
-    ldg8(A.Qin, plane_off(ks), A.vs, q0);
-    ldg8(A.Qin, plane_off(ks + 1), A.vs, q1);
+    ldg8(plane_ptr(ks), 0, A.vs, q0);
+    ldg8(plane_ptr(ks + 1), 0, A.vs, q1);
     hflux(q1, h1);
 #pragma unroll
     for (int v = 0; v < 8; ++v) { qim[v] = 1.0f; qic[v] = 1.0f; }
-    if (first && A.qlo != nullptr) ldg8(A.qlo, lcol, P.plane, qic);  // Qint(ks) == Qint(ka-1)
+    if (first) ldg8(A.qlo, lcol, P.plane, qic);  // Qint(ka-1)
 
+    float* outp = A.Qout + (long long)(ka - A.kbase) * P.plane + lcol;
     for (int k = ks; k < kb; ++k) {
         const int buf = (k - ks) & 1;
         const int kp = k + 1;
         float qn[8], hn[8], qip[8];
-        ldg8(A.Qin, plane_off(k + 2), A.vs, qn);
+        ldg8(plane_ptr(k + 2), 0, A.vs, qn);
         float* bQ = sQ + buf * 8 * TI * 32;
         float* bQi = sQi + buf * 8 * TI * 32;
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
-            bQ[(v * TI + ti) * 32 + lane] = q1[v];
-            bQi[(v * TI + ti) * 32 + lane] = qic[v];
+            bQ[v * TI * 32 + so] = q1[v];
+            bQi[v * TI * 32 + so] = qic[v];
         }
         __syncthreads();
 
-        // ---- predictor plane kp = k+1 ------------------------------------------------------------
+        // ---- predictor plane kp = k+1 (kp >= 1 here: plane 0 is never re-derived in the loop) --------------
         hflux(qn, hn);
         if (kp == A.hi_plane) {
             ldg8(A.qhi, lcol, P.plane, qip);
-        } else if (kp <= P.Nz - 2) {
+        } else {
             float xp[8], yp[8], xm[8], ym[8];
 #pragma unroll
             for (int v = 0; v < 8; ++v) {
-                xp[v] = bQ[(v * TI + tip) * 32 + lane];
+                xp[v] = bQ[v * TI * 32 + sop];
                 yp[v] = __shfl_down_sync(0xffffffffu, q1[v], 1);
             }
-            const bool lap = PATH == IMHD_PATH_B && interior_ij && kp >= 1;
             if (PATH == IMHD_PATH_B) {
 #pragma unroll
                 for (int v = 0; v < 8; ++v) {
-                    xm[v] = bQ[(v * TI + tim) * 32 + lane];
+                    xm[v] = bQ[v * TI * 32 + som];
                     ym[v] = __shfl_up_sync(0xffffffffu, q1[v], 1);
                 }
             }
-            qint_cell<PATH>(q1, xp, yp, h1, hn, xm, ym, q0, qn, bottom, right, kp == 0, lap, P, qip);
-        } else {
-#pragma unroll
-            for (int v = 0; v < 8; ++v) qip[v] = 1.0f;
+            qint_cell<PATH>(q1, xp, yp, h1, hn, xm, ym, q0, qn, bottom, right, false, interior_ij, P, qip);
         }
 
         // ---- corrector plane k -----------------------------------------------------------------------
         if (k >= ka) {
-            float out[8];
-#pragma unroll
-            for (int v = 0; v < 8; ++v) out[v] = q0[v];  // cells no pass touches are carried over
-            float xm[8], ym[8], xp[8], yp[8];
+            float out[8], xm[8], ym[8], xp[8], yp[8];
 #pragma unroll
             for (int v = 0; v < 8; ++v) {
-                xm[v] = bQi[(v * TI + tim) * 32 + lane];
+                xm[v] = bQi[v * TI * 32 + som];
                 ym[v] = __shfl_up_sync(0xffffffffu, qic[v], 1);
             }
             if (PATH == IMHD_PATH_B) {
 #pragma unroll
                 for (int v = 0; v < 8; ++v) {
-                    xp[v] = bQi[(v * TI + tip) * 32 + lane];
+                    xp[v] = bQi[v * TI * 32 + sop];
                     yp[v] = __shfl_down_sync(0xffffffffu, qic[v], 1);
                 }
             }
-            if (PATH == IMHD_PATH_A) {
-                // FluidAdvanceLocalNoDiff: i,j,k >= 1 including the far faces (B-14)
-                if (k >= 1 && in_dom && !top && !left) corr_cell<PATH>(q0, qic, xm, ym, qim, xp, yp, qip, P, out);
-            } else {
-                if (k >= 1 && k <= P.Nz - 2) {
-                    if (interior_ij) corr_cell<PATH>(q0, qic, xm, ym, qim, xp, yp, qip, P, out);
-                } else if (k == 0) {
-                    if (interior_ij) {
-                        front_cell_exact(q0, qic, xm, ym, qim, xp, yp, qip, P, out);
-                    } else if (in_dom && (top || bottom)) {  // walls (0,j,0), (Nx-1,j,0): kernels_fluidbcs.cu:164-188
-                        out[RHO] = 1.0f;
+            corr_cell<PATH>(q0, qic, xm, ym, qim, xp, yp, qip, P, out);
+            if (owner) {
 #pragma unroll
-                        for (int v = 1; v < 7; ++v) out[v] = 0.0f;
-                        float e = q0[EN];
-                        for (int rep = 0; rep < P.Nx; ++rep) {
-                            const float e2 = wall_e(e);
-                            if (e2 == e) break;
-                            e = e2;
-                        }
-                        out[EN] = e;
-                    }
-                } else if (bottom && right) {  // k == Nz-1: only the column (Nx-1,Ny-1) is "periodic" (B-8)
-                    out[RHO] = 1.0f;
-#pragma unroll
-                    for (int v = 1; v < 7; ++v) out[v] = 0.0f;
-                    out[EN] = A.corner_e;
-                }
+                for (int v = 0; v < 8; ++v) outp[v * A.vs] = upd ? out[v] : q0[v];  // untouched cells are carried over
             }
-            // path A never computes plane 0: it is the copy of plane Nz-1 (PBCs), written below or by the exchange
-            if (owner && !(PATH == IMHD_PATH_A && k == 0)) {
-                const long long o = (long long)(k - A.kbase) * P.plane + lcol;
-#pragma unroll
-                for (int v = 0; v < 8; ++v) A.Qout[o + v * A.vs] = out[v];
-                // PBCs (kernels_fluidbcs.cu:498-510): Q[.,.,0] <- Q[.,.,Nz-1]; only when plane 0 is in this array
-                if (PATH == IMHD_PATH_A && k == P.Nz - 1 && A.k0 == 0) {
-                    const long long o0 = (long long)(0 - A.kbase) * P.plane + lcol;
-#pragma unroll
-                    for (int v = 0; v < 8; ++v) A.Qout[o0 + v * A.vs] = out[v];
-                }
-            }
+            outp += P.plane;
         }
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
@@ -316,17 +284,15 @@ __global__ void __launch_bounds__(TI * 32) k_fused_step(const FusedArgs A) {
 // Predictor plane k (global index, k <= Nz-2) into an (8,Nx,Ny) buffer: same device function, same
 // values as the fused kernel computes on chip.
 template <int PATH>
-__global__ void __launch_bounds__(256) k_qint_plane(const FusedArgs A, int k, float* __restrict__ out) {
+__device__ __forceinline__ void qint_at(const FusedArgs& A, int i, int j, int k, float r[8]) {
     const Params& P = A.P;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= P.Nx || j >= P.Ny) return;
     const bool bottom = i == P.Nx - 1, right = j == P.Ny - 1;
     const bool lap = PATH == IMHD_PATH_B && i > 0 && !bottom && j > 0 && !right && k >= 1;
     auto off = [&](int ii, int jj, int kk) -> long long {
         ii = min(max(ii, 0), P.Nx - 1); jj = min(max(jj, 0), P.Ny - 1); kk = min(max(kk, A.kmin), A.kmax);
         return (long long)(kk - A.kbase) * P.plane + (long long)ii * P.Ny + jj;
     };
-    float c[8], xp[8], yp[8], zp[8], xm[8], ym[8], zm[8], hc[8], hp[8], r[8];
+    float c[8], xp[8], yp[8], zp[8], xm[8], ym[8], zm[8], hc[8], hp[8];
     ldg8(A.Qin, off(i, j, k), A.vs, c);
     ldg8(A.Qin, off(i + 1, j, k), A.vs, xp);
     ldg8(A.Qin, off(i, j + 1, k), A.vs, yp);
@@ -337,9 +303,83 @@ __global__ void __launch_bounds__(256) k_qint_plane(const FusedArgs A, int k, fl
     hflux(c, hc);
     hflux(zp, hp);
     qint_cell<PATH>(c, xp, yp, hc, hp, xm, ym, zm, zp, bottom, right, k == 0, lap, P, r);
+}
+
+template <int PATH>
+__global__ void __launch_bounds__(256) k_qint_plane(const FusedArgs A, int k, float* __restrict__ out) {
+    const Params& P = A.P;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= P.Nx || j >= P.Ny) return;
+    float r[8];
+    qint_at<PATH>(A, i, j, k, r);
     const long long l = (long long)i * P.Ny + j;
 #pragma unroll
     for (int v = 0; v < 8; ++v) out[l + v * P.plane] = r[v];
+}
+
+// Path B, plane 0 of the new state: BoundaryConditions (kernels_fluidbcs.cu:32-235), one thread per (i,j).
+//   interior: corrector with indexed fluxes of Qint(0), k-1 -> Nz-2 (qwrap), + dt*numericalDiffusionFront
+//   i = 0, Nx-1: wall values; j = 0, Ny-1 (i interior): carried over (dead code in the reference, B-8)
+__global__ void __launch_bounds__(256) k_front_plane_B(const FusedArgs A) {
+    const Params& P = A.P;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= P.Nx || j >= P.Ny) return;
+    const long long l = (long long)i * P.Ny + j;
+    const long long o = (long long)(0 - A.kbase) * P.plane + l;
+    float q[8], out[8];
+    ldg8(A.Qin, o, A.vs, q);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) out[v] = q[v];
+    if (i > 0 && i < P.Nx - 1) {
+        if (j > 0 && j < P.Ny - 1) {
+            float c[8], xm[8], ym[8], zm[8], xp[8], yp[8], zp[8];
+            ldg8(A.qlo, l, P.plane, c);           // Qint(0)
+            ldg8(A.qlo, l - P.Ny, P.plane, xm);
+            ldg8(A.qlo, l - 1, P.plane, ym);
+            ldg8(A.qlo, l + P.Ny, P.plane, xp);
+            ldg8(A.qlo, l + 1, P.plane, yp);
+            ldg8(A.qwrap, l, P.plane, zm);        // Qint(Nz-2)
+            qint_at<IMHD_PATH_B>(A, i, j, 1, zp);  // Qint(1)
+            front_cell_exact(q, c, xm, ym, zm, xp, yp, zp, P, out);
+        }
+    } else {
+        out[RHO] = 1.0f;
+#pragma unroll
+        for (int v = 1; v < 7; ++v) out[v] = 0.0f;
+        float e = q[EN];
+        for (int rep = 0; rep < P.Nx; ++rep) {
+            const float e2 = wall_e(e);
+            if (e2 == e) break;
+            e = e2;
+        }
+        out[EN] = e;
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) A.Qout[o + v * A.vs] = out[v];
+}
+
+// Path B, plane Nz-1 of the new state: carried over, except the column (Nx-1,Ny-1) which receives the wall
+// value of (Nx-1,Ny-1,0) (kernels_fluidbcs.cu:227-231, B-8).
+__global__ void __launch_bounds__(256) k_back_plane_B(const FusedArgs A) {
+    const Params& P = A.P;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.plane) return;
+    const long long o = (long long)(P.Nz - 1 - A.kbase) * P.plane + c;
+    const bool corner = c == P.plane - 1;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        float x = __ldg(A.Qin + o + v * A.vs);
+        if (corner) x = v == RHO ? 1.0f : (v == EN ? A.corner_e : 0.0f);
+        A.Qout[o + v * A.vs] = x;
+    }
+}
+
+// dst plane <- src plane of the same array, 8 variables (path A PBCs on the new state)
+__global__ void __launch_bounds__(256) k_plane_copy(float* __restrict__ Q, long long dst, long long src, long long plane, long long vs) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= plane) return;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) Q[dst + c + v * vs] = Q[src + c + v * vs];
 }
 
 }  // namespace imhd
@@ -347,12 +387,12 @@ __global__ void __launch_bounds__(256) k_qint_plane(const FusedArgs A, int k, fl
 using namespace imhd;
 
 static int fill_args(FusedArgs& A, const float* Qin, float* Qout, const float* qlo, const float* qhi,
-                     const imhd_slab* s) {
+                     const float* qwrap, const imhd_slab* s) {
     if (!s) { set_error("null slab descriptor"); return IMHD_E_INVALID; }
     if (int e = bad_dims(s->Nx, s->Ny, s->Nz)) return e;
     if (s->path != IMHD_PATH_A && s->path != IMHD_PATH_B) { set_error("bad path %d", s->path); return IMHD_E_INVALID; }
-    if (s->k0 < 0 || s->nzl < 2 || s->k0 + s->nzl > s->Nz) {
-        set_error("bad slab: k0=%d nzl=%d Nz=%d (need nzl >= 2)", s->k0, s->nzl, s->Nz);
+    if (s->k0 < 0 || s->nzl < 3 || s->k0 + s->nzl > s->Nz) {
+        set_error("bad slab: k0=%d nzl=%d Nz=%d (need nzl >= 3)", s->k0, s->nzl, s->Nz);
         return IMHD_E_INVALID;
     }
     if (!s->ghosts && (s->k0 != 0 || s->nzl != s->Nz)) {
@@ -367,15 +407,18 @@ static int fill_args(FusedArgs& A, const float* Qin, float* Qout, const float* q
     A.kmin = max(s->k0 - g, 0);
     A.kmax = min(s->k0 + s->nzl - 1 + g, s->Nz - 1);
     A.k0 = s->k0; A.k1 = s->k0 + s->nzl;
-    A.qlo = qlo; A.qhi = qhi;
+    A.ka0 = max(A.k0, 1);
+    A.kb0 = min(A.k1, s->path == IMHD_PATH_A ? s->Nz : s->Nz - 1);
+    A.qlo = qlo; A.qhi = qhi; A.qwrap = qwrap;
     A.hi_plane = min(A.k1, s->Nz - 1);
-    A.corner_e = 0.0f;
+    A.corner_e = s->corner_e;
+    A.chunk = 0; A.ntile_i = A.ntile_j = 0;
     return 0;
 }
 
 extern "C" int imhd_qint_plane(const float* Q, float* out_plane, int k, const imhd_slab* s, void* stream) {
     FusedArgs A;
-    if (int e = fill_args(A, Q, nullptr, nullptr, nullptr, s)) return e;
+    if (int e = fill_args(A, Q, nullptr, nullptr, nullptr, nullptr, s)) return e;
     if (k < 0 || k > s->Nz - 2 || k < A.kmin || k + 1 > A.kmax) {
         set_error("imhd_qint_plane: plane %d not computable from array planes [%d,%d]", k, A.kmin, A.kmax);
         return IMHD_E_INVALID;
@@ -397,6 +440,9 @@ extern "C" float imhd_wall_energy_fixed_point(float e, int max_iter) {
     return e;
 }
 
+static int g_chunk_override = 0;
+extern "C" void imhd_set_chunk(int planes) { g_chunk_override = planes; }
+
 template <int PATH, int TI>
 static int launch_fused(FusedArgs& A, cudaStream_t st) {
     constexpr int O = Ring<PATH>::O;
@@ -406,21 +452,21 @@ static int launch_fused(FusedArgs& A, cudaStream_t st) {
     const int ni = PATH == IMHD_PATH_A ? P.Nx - 1 : P.Nx - 2, nj = PATH == IMHD_PATH_A ? P.Ny - 1 : P.Ny - 2;
     A.ntile_i = (ni + WI - 1) / WI;
     A.ntile_j = (nj + WJ - 1) / WJ;
-    const int nzl = A.k1 - A.k0;
+    const int nz = A.kb0 - A.ka0;
+    if (nz <= 0) return 0;
     // chunk length: enough chunks for several waves of blocks, long enough to amortise the 2 warm-up planes
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (long long)A.ntile_i * A.ntile_j;
     int nchunk = (int)((8LL * sms + tiles - 1) / tiles);
-    int chunk = (nzl + nchunk - 1) / nchunk;
+    int chunk = (nz + nchunk - 1) / nchunk;
     if (chunk < 16) chunk = 16;
-    if (chunk > nzl) chunk = nzl;
-    if (A.chunk > 0) chunk = min(A.chunk, nzl);  // caller override (tests)
+    if (g_chunk_override > 0) chunk = g_chunk_override;
     if (chunk < 2) chunk = 2;
+    if (chunk > nz) chunk = nz;
     A.chunk = chunk;
-    nchunk = (nzl + chunk - 1) / chunk;
-    // a trailing chunk of one plane would start its warm-up before the previous chunk's first plane: fine
+    nchunk = (nz + chunk - 1) / chunk;
     const size_t smem = 2 * 2 * 8 * TI * 32 * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
@@ -433,22 +479,36 @@ static int launch_fused(FusedArgs& A, cudaStream_t st) {
     return 0;
 }
 
-static int g_chunk_override = 0;
-extern "C" void imhd_set_chunk(int planes) { g_chunk_override = planes; }
-
 extern "C" int imhd_step_fused(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
-                               const imhd_slab* s, void* stream) {
+                               const float* qint_wrap, const imhd_slab* s, void* stream) {
     FusedArgs A;
-    if (int e = fill_args(A, Qin, Qout, qint_lo, qint_hi, s)) return e;
+    if (int e = fill_args(A, Qin, Qout, qint_lo, qint_hi, qint_wrap, s)) return e;
     if (Qin == Qout) { set_error("imhd_step_fused: Qin and Qout must be distinct buffers"); return IMHD_E_INVALID; }
-    if (!qint_hi || (s->path == IMHD_PATH_B && !qint_lo) || (s->k0 > 0 && !qint_lo)) {
-        set_error("imhd_step_fused: missing predictor ghost plane (qint_lo=%p qint_hi=%p)", (const void*)qint_lo, (const void*)qint_hi);
+    if (!qint_lo || !qint_hi || (s->path == IMHD_PATH_B && s->k0 == 0 && !qint_wrap)) {
+        set_error("imhd_step_fused: missing predictor plane (qint_lo=%p qint_hi=%p qint_wrap=%p)", (const void*)qint_lo,
+                  (const void*)qint_hi, (const void*)qint_wrap);
         return IMHD_E_INVALID;
     }
-    A.corner_e = s->corner_e;
-    A.chunk = g_chunk_override;
     cudaStream_t st = (cudaStream_t)stream;
-    if (s->path == IMHD_PATH_A) return launch_fused<IMHD_PATH_A, 16>(A, st);
-    return launch_fused<IMHD_PATH_B, 16>(A, st);
+    const Params& P = A.P;
+    const unsigned pb = (unsigned)((P.plane + 255) / 256);
+    if (s->path == IMHD_PATH_A) {
+        if (int e = launch_fused<IMHD_PATH_A, 16>(A, st)) return e;
+        if (A.k0 == 0 && A.k1 == P.Nz) {  // PBCs on one GPU; across slabs the ghost exchange carries this plane
+            k_plane_copy<<<pb, 256, 0, st>>>(Qout, (long long)(0 - A.kbase) * P.plane, (long long)(P.Nz - 1 - A.kbase) * P.plane,
+                                             P.plane, A.vs);
+            IMHD_LAUNCH_CHECK(1);
+        }
+        return 0;
+    }
+    if (int e = launch_fused<IMHD_PATH_B, 16>(A, st)) return e;
+    if (A.k0 == 0) {
+        k_front_plane_B<<<dim3((P.Ny + 31) / 32, (P.Nx + 7) / 8), dim3(32, 8), 0, st>>>(A);
+        IMHD_LAUNCH_CHECK(1);
+    }
+    if (A.k1 == P.Nz) {
+        k_back_plane_B<<<pb, 256, 0, st>>>(A);
+        IMHD_LAUNCH_CHECK(1);
+    }
+    return 0;
 }
-

@@ -115,10 +115,11 @@ def qint_plane(Q, k, slab: Slab, out=None):
     return out
 
 
-def step_fused(Qin, Qout, qint_lo, qint_hi, slab: Slab):
+def step_fused(Qin, Qout, qint_lo, qint_hi, qint_wrap, slab: Slab):
     L = _lib.load()
-    lo = _dev(qint_lo) if qint_lo is not None else None
-    check(L.imhd_step_fused(_dev(Qin), _dev(Qout, Qin.shape), lo, _dev(qint_hi), C.byref(slab), _stream()))
+    wrap = _dev(qint_wrap) if qint_wrap is not None else None
+    check(L.imhd_step_fused(_dev(Qin), _dev(Qout, Qin.shape), _dev(qint_lo), _dev(qint_hi), wrap, C.byref(slab),
+                            _stream()))
 
 
 def wall_energy_fixed_point(e: float, max_iter: int) -> float:
@@ -129,9 +130,9 @@ def step_full_domain(Qin, Qout, path, D, dt, dx, dy, dz, corner_e=0.0):
     """One fused step of a whole-domain (8,Nz,Nx,Ny) array on one GPU, including the periodic wrap planes."""
     Nx, Ny, Nz = _dims(Qin)
     s = make_slab(Nx, Ny, Nz, path, D, dt, dx, dy, dz, corner_e=corner_e)
-    lo = qint_plane(Qin, Nz - 2, s)
-    hi = qint_plane(Qin, 0, s)
-    step_fused(Qin, Qout, lo, hi, s)
+    q0 = qint_plane(Qin, 0, s)  # Qint(0) == Qint(Nz-1): both ends of the slab
+    wrap = qint_plane(Qin, Nz - 2, s) if path == PATH_B else None
+    step_fused(Qin, Qout, q0, q0, wrap, s)
 
 
 def launch_count() -> int:

@@ -6,7 +6,8 @@ planes [k0, k1) and stores them with one ghost plane on each side as an (8, nzl+
 
 Per time step and rank (ring neighbours, periodic in z):
   1. compute the two predictor planes the neighbours need (``imhd_qint_plane``) and exchange them:
-       up-going   Qint(k1-1)   -> rank r+1's ``qint_lo``   (the last rank sends Qint(Nz-2): Qint(-1) == Qint(Nz-2))
+       up-going   Qint(k1-1)   -> rank r+1's ``qint_lo``   (the last rank sends Qint(Nz-2) == Qint(-1), which
+                                  rank 0 uses as ``qint_wrap`` for the k=0 face; rank 0's ``qint_lo`` is its own Qint(0))
        down-going Qint(k0)     -> rank r-1's ``qint_hi``   (rank 0 sends Qint(0): Qint(Nz-1) == Qint(0))
   2. one fused kernel over the owned planes (``imhd_step_fused``)
   3. exchange the new boundary planes of Q into the neighbours' ghost planes; for path A the plane the
@@ -141,12 +142,19 @@ class SlabSolver:
         L, c = self.layout, self.compute
         Q = self.Q[self.cur]
         if self.comm is None or L.world == 1:
-            c.qint_plane(Q, self.Nz - 2, self.slab, out=self.qint_lo)
-            c.qint_plane(Q, 0, self.slab, out=self.qint_hi)
+            c.qint_plane(Q, 0, self.slab, out=self.qint_hi)          # Qint(0) == Qint(Nz-1)
+            self.lo, self.hi, self.wrap = self.qint_hi, self.qint_hi, None
+            if self.path == PATH_B:
+                c.qint_plane(Q, self.Nz - 2, self.slab, out=self.qint_lo)  # Qint(Nz-2) == Qint(-1)
+                self.wrap = self.qint_lo
             return
         c.qint_plane(Q, L.up_plane, self.slab, out=self.send_up)
         c.qint_plane(Q, L.down_plane, self.slab, out=self.send_down)
         self.comm.ring_exchange(self.send_up, self.send_down, self.qint_lo, self.qint_hi, L.up, L.down)
+        if L.rank == 0:  # received Qint(Nz-2) from the last rank; the plane below plane 1 is this rank's own Qint(0)
+            self.lo, self.hi, self.wrap = self.send_down, self.qint_hi, self.qint_lo
+        else:
+            self.lo, self.hi, self.wrap = self.qint_lo, self.qint_hi, None
 
     def exchange_ghosts(self):
         """New boundary planes of Q -> neighbours' ghost planes (+ the path A periodic copy)."""
@@ -169,8 +177,7 @@ class SlabSolver:
         for _ in range(nsteps):
             self.exchange_qint()
             Qin, Qout = self.Q[self.cur], self.Q[1 - self.cur]
-            lo = self.qint_lo if (self.path == PATH_B or self.layout.k0 > 0) else None
-            self.compute.step_fused(Qin, Qout, lo, self.qint_hi, self.slab)
+            self.compute.step_fused(Qin, Qout, self.lo, self.hi, self.wrap, self.slab)
             self.cur = 1 - self.cur
             self.exchange_ghosts()
 

@@ -102,9 +102,13 @@ int imhd_init_cubic_bennett_vortex_m0(float* Q, float k, float A, const float* x
  * Slab form (z-slab domain decomposition, one slab per GPU): the buffers hold global planes
  * [k0-1, k0+nzl] -- nzl owned planes plus one ghost plane on each side -- as a
  * (8, nzl+2, Nx, Ny) array; pass k0 = 0, nzl = Nz and ghosts = 0 for a plain (8,Nz,Nx,Ny)
- * full-domain array.  qint_lo / qint_hi are the (8,Nx,Ny) predictor planes just below and
- * just above the slab (periodic in z with period Nz-1), produced by imhd_qint_plane on the
- * neighbouring rank (or on this one when the slab touches both ends). */
+ * full-domain array.  The (8,Nx,Ny) predictor planes at the slab ends are inputs, produced by
+ * imhd_qint_plane on the neighbouring rank (or on this one where the slab touches a domain end;
+ * Qint is periodic in z with period Nz-1):
+ *   qint_lo   = Qint(k0-1), or this slab's own Qint(0) when k0 == 0
+ *   qint_hi   = Qint(k0+nzl), or Qint(0) (== Qint(Nz-1)) when the slab ends the domain
+ *   qint_wrap = Qint(Nz-2) (== Qint(-1)); only read for path B on the slab with k0 == 0 (k=0 face)
+ * On one GPU: qint_lo = qint_hi = Qint(0), qint_wrap = Qint(Nz-2). */
 typedef struct {
     int Nx, Ny, Nz;     /* global grid                                        */
     int k0, nzl;        /* first owned global plane, number of owned planes   */
@@ -117,7 +121,7 @@ typedef struct {
 } imhd_slab;
 
 int imhd_step_fused(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
-                    const imhd_slab* s, void* stream);
+                    const float* qint_wrap, const imhd_slab* s, void* stream);
 
 /* e <- p(e,0,0)/(gamma-1) iterated to its fixed point (lib/on-device/kernels_fluidbcs.cu:173,187; every
  * x-thread of the reference launch re-applies it).  Scalar host helper, identity when e == 0. */

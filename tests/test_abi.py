@@ -69,5 +69,5 @@ def test_bad_arguments_are_rejected(imhd):
     lib = imhd._lib.load()
     assert lib.imhd_predictor(None, None, 0, 0.0, 1e-4, 0.1, 0.1, 0.1, 2, 16, 16, None) == imhd._lib.E_INVALID
     s = imhd.ops.make_slab(16, 16, 16, 0, 0.0, 1e-4, 0.1, 0.1, 0.1, k0=4, nzl=4, ghosts=0)
-    assert lib.imhd_step_fused(None, None, None, None, C.byref(s), None) == imhd._lib.E_INVALID
+    assert lib.imhd_step_fused(None, None, None, None, None, C.byref(s), None) == imhd._lib.E_INVALID
     assert "ghosts" in lib.imhd_last_error().decode()
