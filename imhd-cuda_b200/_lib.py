@@ -46,6 +46,7 @@ SIGNATURES = {
     "imhd_step_fused": (_i, [_p, _p, _p, _p, _p, C.POINTER(Slab), _p]),
     "imhd_wall_energy_fixed_point": (_f, [_f, _i]),
     "imhd_set_chunk": (None, [_i]),
+    "imhd_set_kernel_variant": (None, [_i]),
     "imhd_qint_plane": (_i, [_p, _p, _i, C.POINTER(Slab), _p]),
     "imhd_create": (_p, _dims + [_i]),
     "imhd_destroy": (None, [_p]),

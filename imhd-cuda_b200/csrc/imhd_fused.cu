@@ -28,6 +28,9 @@
 // -fmad=false and every fused multiply-add is written out, so a value depends only on its inputs,
 // never on which kernel/block computed it: results are bit-identical for any chunking or slab
 // decomposition.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "imhd_common.cuh"
 
 namespace imhd {
@@ -169,10 +172,12 @@ __device__ __forceinline__ void front_cell_exact(const float q[8], const float c
 }
 
 // -----------------------------------------------------------------------------------------------
-// The fused z-marching kernel: planes [ka0, kb0) of the slab.
+// The fused z-marching kernel, plain-load variant: planes [ka0, kb0) of the slab.  Used when the
+// grid does not meet TMA's 16-byte row-stride rule (Ny % 4 != 0); same device functions, same bits
+// as the TMA variant below.
 // -----------------------------------------------------------------------------------------------
 template <int PATH, int TI>
-__global__ void __launch_bounds__(TI * 32, 1) k_fused_step(const FusedArgs A) {
+__global__ void __launch_bounds__(TI * 32, 1) k_fused_step_ldg(const FusedArgs A) {
     constexpr int O = Ring<PATH>::O;
     constexpr int WI = TI - 2 * O, WJ = 32 - 2 * O;
     extern __shared__ float smem[];
@@ -279,6 +284,229 @@ __global__ void __launch_bounds__(TI * 32, 1) k_fused_step(const FusedArgs A) {
             qim[v] = qic[v]; qic[v] = qip[v];
         }
     }
+}
+
+// -----------------------------------------------------------------------------------------------
+// The fused z-marching kernel, TMA variant (the hot path).
+//
+//   - thread tile = the region where the predictor is evaluated: TI x 32 cells, one column per thread
+//   - per plane ONE cp.async.bulk.tensor (4-D box: 40 x (TI+2) x 1 plane x 8 variables, 23 KB) stages the Q
+//     tile INCLUDING a one-cell ring around the thread tile into shared memory; out-of-domain elements are
+//     zero-filled by the hardware and only ever feed lanes whose results are discarded.  Three stages
+//     (planes k+1, k+2 resident, k+3 in flight), one mbarrier each; the stage of plane k is recycled right
+//     after the per-plane __syncthreads.
+//   - own-column queue in registers: Q(k), Q(k+1), H(Q(k+1)), Qint(k-1), Qint(k); Q(k+2) is read from the
+//     tile; the four lateral neighbours of Q(k+1) come from the tile, those of Qint(k) from a
+//     double-buffered exchange array (i+-1) and warp shuffles (j+-1)
+//   - the corrector is written for ti in [1, TI-2], lane in [1, 30] (path B; one more row/lane for path A):
+//     14x30 of 16x32 threads produce output (82 %), tiles overlap by the one-cell Qint ring
+//   - the k loop is unrolled by 3 so that stage indices are static and the register queue rotates by renaming
+// -----------------------------------------------------------------------------------------------
+constexpr int kTC = 40;  // tile columns: 32 + 2 ring + up to 3 of alignment slack (a TMA box must START on a 16-byte boundary)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(0)
+        : "memory");
+}
+
+template <int PATH, int TI>
+struct TmaGeo {
+    static constexpr int TR = TI + 2;                                   // tile rows
+    static constexpr int WI = PATH == IMHD_PATH_A ? TI - 1 : TI - 2;    // output rows per tile
+    static constexpr int WJ = PATH == IMHD_PATH_A ? 31 : 30;            // output lanes per tile
+    static constexpr int STAGE_FLOATS = 8 * TR * kTC;
+    static constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
+    static constexpr int XCH_FLOATS = 2 * 8 * TI * 32;
+    static constexpr size_t SMEM = 3 * STAGE_BYTES + XCH_FLOATS * 4 + 64;
+};
+
+template <int PATH, int TI>
+struct TmaThread {  // per-thread constants of the TMA kernel
+    bool bottom, right, interior_ij, upd, owner, corr_row;
+    int own, so, som, sop;  // tile offset of the own cell; exchange slots own / i-1 / i+1
+    long long lcol;
+};
+
+// One plane of the march: predictor plane k+1, corrector plane k.  tq1 / tq2 = tiles of planes k+1 / k+2.
+template <int PATH, int TI>
+__device__ __forceinline__ void tma_plane(const FusedArgs& A, const TmaThread<PATH, TI>& T, int k, int ka, const float* tq1,
+                                          const float* tq2, float* xq, const float (&q0)[8], const float (&q1)[8],
+                                          float (&qn)[8], const float (&h1)[8], float (&hn)[8], const float (&qim)[8],
+                                          const float (&qic)[8], float (&qip)[8], float*& outp) {
+    using G = TmaGeo<PATH, TI>;
+    const Params& P = A.P;
+    constexpr int VS = G::TR * kTC;  // variable stride inside a tile
+#pragma unroll
+    for (int v = 0; v < 8; ++v) qn[v] = tq2[v * VS + T.own];
+    hflux(qn, hn);
+    if (k + 1 == A.hi_plane) {
+        ldg8(A.qhi, T.lcol, P.plane, qip);
+    } else {
+        float xp[8], yp[8], xm[8], ym[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            xp[v] = tq1[v * VS + T.own + kTC];
+            yp[v] = tq1[v * VS + T.own + 1];
+        }
+        if (PATH == IMHD_PATH_B) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                xm[v] = tq1[v * VS + T.own - kTC];
+                ym[v] = tq1[v * VS + T.own - 1];
+            }
+        }
+        qint_cell<PATH>(q1, xp, yp, h1, hn, xm, ym, q0, qn, T.bottom, T.right, false, T.interior_ij, P, qip);
+    }
+    if (k >= ka) {
+        if (T.corr_row) {  // warp-uniform: the first (and for path B the last) row of the tile only feeds its neighbours
+            float out[8], xm[8], ym[8], xp[8], yp[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                xm[v] = xq[v * TI * 32 + T.som];
+                ym[v] = __shfl_up_sync(0xffffffffu, qic[v], 1);
+            }
+            if (PATH == IMHD_PATH_B) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    xp[v] = xq[v * TI * 32 + T.sop];
+                    yp[v] = __shfl_down_sync(0xffffffffu, qic[v], 1);
+                }
+            }
+            corr_cell<PATH>(q0, qic, xm, ym, qim, xp, yp, qip, P, out);
+            if (T.owner) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) outp[v * A.vs] = T.upd ? out[v] : q0[v];  // untouched cells are carried over
+            }
+        } else if (T.owner) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) outp[v * A.vs] = q0[v];
+        }
+        outp += P.plane;
+    }
+}
+
+template <int PATH, int TI>
+__global__ void __launch_bounds__(TI * 32, 1) k_fused_step_tma(const FusedArgs A, const __grid_constant__ CUtensorMap tmap) {
+    using G = TmaGeo<PATH, TI>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* tiles = reinterpret_cast<float*>(smem_raw);                       // [3][8][TR][kTC]
+    float* xch = tiles + 3 * G::STAGE_FLOATS;                                 // [2][8][TI][32]  Qint exchange
+    uint64_t* full = reinterpret_cast<uint64_t*>(xch + G::XCH_FLOATS);        // [3]
+
+    const Params& P = A.P;
+    const int lane = threadIdx.x, ti = threadIdx.y;
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    const int ib = bi * G::WI, jb = bj * G::WJ;
+    const int i = ib + ti, j = jb + lane;
+    const bool in_dom = i < P.Nx && j < P.Ny;
+    TmaThread<PATH, TI> T;
+    T.bottom = (i == P.Nx - 1);
+    T.right = (j == P.Ny - 1);
+    T.interior_ij = in_dom && i > 0 && !T.bottom && j > 0 && !T.right;
+    T.upd = PATH == IMHD_PATH_A ? (in_dom && i > 0 && j > 0) : T.interior_ij;
+    const int oi_lo = bi == 0 ? 0 : ib + 1, oi_hi = bi == A.ntile_i - 1 ? P.Nx : ib + G::WI + 1;
+    const int oj_lo = bj == 0 ? 0 : jb + 1, oj_hi = bj == A.ntile_j - 1 ? P.Ny : jb + G::WJ + 1;
+    T.owner = in_dom && i >= oi_lo && i < oi_hi && j >= oj_lo && j < oj_hi;
+    T.corr_row = ti >= 1 && (PATH == IMHD_PATH_A || ti <= TI - 2);
+    // the box starts at the 4-column boundary at or below jb-1 (measured: a misaligned inner coordinate traps)
+    const int c0 = ((jb - 1 + 4) / 4) * 4 - 4;
+    T.own = (ti + 1) * kTC + (jb - 1 - c0) + lane + 1;
+    T.so = ti * 32 + lane;
+    T.som = max(ti - 1, 0) * 32 + lane;
+    T.sop = min(ti + 1, TI - 1) * 32 + lane;
+    T.lcol = (long long)min(i, P.Nx - 1) * P.Ny + min(j, P.Ny - 1);
+
+    const int ka = A.ka0 + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kb0);
+    const bool first = blockIdx.z == 0;
+    const int ks = first ? ka - 1 : ka - 2;
+    const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
+    const int klast = kb + 1;  // last plane any iteration reads
+
+    auto issue = [&](int plane, int stage) {  // producer only
+        const int kc = min(max(plane, A.kmin), A.kmax) - A.kbase;
+        mbar_expect_tx(&full[stage], G::STAGE_BYTES);
+        tma_load_tile(tiles + stage * G::STAGE_FLOATS, &tmap, &full[stage], c0, ib - 1, kc);
+    };
+
+    if (producer) {
+        for (int s = 0; s < 3; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+    if (producer)
+        for (int s = 0; s < 3; ++s) issue(ks + s, s);
+
+    float qa[8], qb[8], qc[8], ha[8], hb[8], hc[8], ia[8], ib_[8], ic[8];
+    constexpr int VS = G::TR * kTC;
+    mbar_wait(&full[0], 0);
+    mbar_wait(&full[1], 0);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        qa[v] = tiles[v * VS + T.own];
+        qb[v] = tiles[G::STAGE_FLOATS + v * VS + T.own];
+        ia[v] = 1.0f;
+        ib_[v] = 1.0f;
+    }
+    hflux(qb, hb);
+    if (first) ldg8(A.qlo, T.lcol, P.plane, ib_);  // Qint(ka-1)
+
+    float* outp = A.Qout + (long long)(ka - A.kbase) * P.plane + T.lcol;
+    float* t0 = tiles;
+    float* t1 = tiles + G::STAGE_FLOATS;
+    float* t2 = tiles + 2 * G::STAGE_FLOATS;
+    float* x0 = xch;
+    float* x1 = xch + 8 * TI * 32;
+
+    // one step of the march; roles (Q(k),Q(k+1),Q(k+2)) / (H(k+1),H(k+2)) / (Qint(k-1),Qint(k),Qint(k+1)) / tiles rotate by renaming
+#define IMHD_MARCH(IT, Q0, Q1, QN, H1, HN, IM, IC, IP, TFREE, TQ1, TQ2, SFREE, S2)                       \
+    if (k < kb) {                                                                                         \
+        float* xq = ((IT)&1) ? x1 : x0;                                                                   \
+        _Pragma("unroll") for (int v = 0; v < 8; ++v) xq[v * TI * 32 + T.so] = IC[v];                     \
+        mbar_wait(&full[S2], par##S2);                                                                    \
+        par##S2 ^= 1;                                                                                     \
+        __syncthreads();                                                                                  \
+        if (producer && k + 3 <= klast) issue(k + 3, SFREE);                                              \
+        tma_plane<PATH, TI>(A, T, k, ka, TQ1, TQ2, xq, Q0, Q1, QN, H1, HN, IM, IC, IP, outp);            \
+        ++k;                                                                                              \
+    }
+
+    // parity of the NEXT wait on each stage: stages 0,1 were waited once in the prologue
+    uint32_t par0 = 1, par1 = 1, par2 = 0;
+    int k = ks;
+    while (k < kb) {
+        // it % 6 pattern: exchange buffer alternates (period 2), stages rotate (period 3)
+        IMHD_MARCH(0, qa, qb, qc, hb, hc, ia, ib_, ic, t0, t1, t2, 0, 2)
+        IMHD_MARCH(1, qb, qc, qa, hc, ha, ib_, ic, ia, t1, t2, t0, 1, 0)
+        IMHD_MARCH(2, qc, qa, qb, ha, hb, ic, ia, ib_, t2, t0, t1, 2, 1)
+        IMHD_MARCH(3, qa, qb, qc, hb, hc, ia, ib_, ic, t0, t1, t2, 0, 2)
+        IMHD_MARCH(4, qb, qc, qa, hc, ha, ib_, ic, ia, t1, t2, t0, 1, 0)
+        IMHD_MARCH(5, qc, qa, qb, ha, hb, ic, ia, ib_, t2, t0, t1, 2, 1)
+    }
+#undef IMHD_MARCH
 }
 
 // Predictor plane k (global index, k <= Nz-2) into an (8,Nx,Ny) buffer: same device function, same
@@ -443,17 +671,39 @@ extern "C" float imhd_wall_energy_fixed_point(float e, int max_iter) {
 static int g_chunk_override = 0;
 extern "C" void imhd_set_chunk(int planes) { g_chunk_override = planes; }
 
-template <int PATH, int TI>
-static int launch_fused(FusedArgs& A, cudaStream_t st) {
-    constexpr int O = Ring<PATH>::O;
-    constexpr int WI = TI - 2 * O, WJ = 32 - 2 * O;
+// ---- TMA descriptor ----------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled get_encode() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled)p;
+    }
+    return fn;
+}
+
+static int g_force_ldg = 0;
+extern "C" void imhd_set_kernel_variant(int force_plain_loads) { g_force_ldg = force_plain_loads; }
+
+// 4-D view (j, i, plane, variable) of a state array for the tile loads of the TMA kernel.
+static bool make_tile_map(CUtensorMap* map, const FusedArgs& A, int nplanes, int tile_rows) {
     const Params& P = A.P;
-    // cells needing a thread in the inner window: i in [1, Nx-1] (A) / [1, Nx-2] (B); edges ride along
-    const int ni = PATH == IMHD_PATH_A ? P.Nx - 1 : P.Nx - 2, nj = PATH == IMHD_PATH_A ? P.Ny - 1 : P.Ny - 2;
-    A.ntile_i = (ni + WI - 1) / WI;
-    A.ntile_j = (nj + WJ - 1) / WJ;
-    const int nz = A.kb0 - A.ka0;
-    if (nz <= 0) return 0;
+    PFN_cuTensorMapEncodeTiled enc = get_encode();
+    if (!enc || g_force_ldg) return false;
+    if (P.Ny % 4 != 0 || ((uintptr_t)A.Qin & 15) != 0) return false;  // TMA: 16-byte base and strides
+    const cuuint64_t dims[4] = {(cuuint64_t)P.Ny, (cuuint64_t)P.Nx, (cuuint64_t)nplanes, 8};
+    const cuuint64_t strides[3] = {(cuuint64_t)P.Ny * 4, (cuuint64_t)P.plane * 4, (cuuint64_t)A.vs * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)kTC, (cuuint32_t)tile_rows, 1, 8};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)A.Qin, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int pick_chunk(FusedArgs& A, int nz) {
     // chunk length: enough chunks for several waves of blocks, long enough to amortise the 2 warm-up planes
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -466,15 +716,43 @@ static int launch_fused(FusedArgs& A, cudaStream_t st) {
     if (chunk < 2) chunk = 2;
     if (chunk > nz) chunk = nz;
     A.chunk = chunk;
-    nchunk = (nz + chunk - 1) / chunk;
+    return (nz + chunk - 1) / chunk;
+}
+
+template <int PATH, int TI>
+static int launch_fused(FusedArgs& A, int nplanes_array, cudaStream_t st) {
+    const Params& P = A.P;
+    const int nz = A.kb0 - A.ka0;
+    if (nz <= 0) return 0;
+    // cells the corrector updates, counted from index 1: i in [1, Nx-1] (A) / [1, Nx-2] (B); edge cells ride along
+    const int ni = PATH == IMHD_PATH_A ? P.Nx - 1 : P.Nx - 2, nj = PATH == IMHD_PATH_A ? P.Ny - 1 : P.Ny - 2;
+    CUtensorMap tmap;
+    if (make_tile_map(&tmap, A, nplanes_array, TmaGeo<PATH, TI>::TR)) {
+        using G = TmaGeo<PATH, TI>;
+        A.ntile_i = (ni + G::WI - 1) / G::WI;
+        A.ntile_j = (nj + G::WJ - 1) / G::WJ;
+        const int nchunk = pick_chunk(A, nz);
+        static bool attr_set = false;
+        if (!attr_set) {
+            IMHD_CUDA(cudaFuncSetAttribute(k_fused_step_tma<PATH, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+            attr_set = true;
+        }
+        k_fused_step_tma<PATH, TI><<<dim3(A.ntile_j, A.ntile_i, nchunk), dim3(32, TI), G::SMEM, st>>>(A, tmap);
+        IMHD_LAUNCH_CHECK(1);
+        return 0;
+    }
+    constexpr int O = Ring<PATH>::O;
+    constexpr int WI = TI - 2 * O, WJ = 32 - 2 * O;
+    A.ntile_i = (ni + WI - 1) / WI;
+    A.ntile_j = (nj + WJ - 1) / WJ;
+    const int nchunk = pick_chunk(A, nz);
     const size_t smem = 2 * 2 * 8 * TI * 32 * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
-        IMHD_CUDA(cudaFuncSetAttribute(k_fused_step<PATH, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IMHD_CUDA(cudaFuncSetAttribute(k_fused_step_ldg<PATH, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const dim3 grid(A.ntile_j, A.ntile_i, nchunk), block(32, TI);
-    k_fused_step<PATH, TI><<<grid, block, smem, st>>>(A);
+    k_fused_step_ldg<PATH, TI><<<dim3(A.ntile_j, A.ntile_i, nchunk), dim3(32, TI), smem, st>>>(A);
     IMHD_LAUNCH_CHECK(1);
     return 0;
 }
@@ -493,7 +771,7 @@ extern "C" int imhd_step_fused(const float* Qin, float* Qout, const float* qint_
     const Params& P = A.P;
     const unsigned pb = (unsigned)((P.plane + 255) / 256);
     if (s->path == IMHD_PATH_A) {
-        if (int e = launch_fused<IMHD_PATH_A, 16>(A, st)) return e;
+        if (int e = launch_fused<IMHD_PATH_A, 16>(A, s->nzl + 2 * (s->ghosts ? 1 : 0), st)) return e;
         if (A.k0 == 0 && A.k1 == P.Nz) {  // PBCs on one GPU; across slabs the ghost exchange carries this plane
             k_plane_copy<<<pb, 256, 0, st>>>(Qout, (long long)(0 - A.kbase) * P.plane, (long long)(P.Nz - 1 - A.kbase) * P.plane,
                                              P.plane, A.vs);
@@ -501,7 +779,7 @@ extern "C" int imhd_step_fused(const float* Qin, float* Qout, const float* qint_
         }
         return 0;
     }
-    if (int e = launch_fused<IMHD_PATH_B, 16>(A, st)) return e;
+    if (int e = launch_fused<IMHD_PATH_B, 16>(A, s->nzl + 2 * (s->ghosts ? 1 : 0), st)) return e;
     if (A.k0 == 0) {
         k_front_plane_B<<<dim3((P.Ny + 31) / 32, (P.Nx + 7) / 8), dim3(32, 8), 0, st>>>(A);
         IMHD_LAUNCH_CHECK(1);

@@ -127,8 +127,10 @@ int imhd_step_fused(const float* Qin, float* Qout, const float* qint_lo, const f
  * x-thread of the reference launch re-applies it).  Scalar host helper, identity when e == 0. */
 float imhd_wall_energy_fixed_point(float e, int max_iter);
 
-/* Test hook: force the z-chunk length of the fused kernel (0 = automatic). */
+/* Test hooks: force the z-chunk length of the fused kernel (0 = automatic); force the plain-load
+ * variant of the fused kernel instead of the TMA one (both give the same bits). */
 void imhd_set_chunk(int planes);
+void imhd_set_kernel_variant(int force_plain_loads);
 
 /* Predictor plane Qint(.,.,k) for one owned global plane k into an (8,Nx,Ny) device buffer
  * (the data a neighbouring slab needs as qint_lo / qint_hi). */

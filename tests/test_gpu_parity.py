@@ -214,6 +214,22 @@ def test_fused_is_chunking_independent(imhd, torch, O, oracle_mod):
             assert bits_equal(run_fused(imhd, Q0, path, D, DT, d, 6, chunk=chunk), ref), (path, chunk)
 
 
+def test_tma_and_plain_load_variants_give_the_same_bits(imhd, torch, O, oracle_mod):
+    """The hot kernel stages Q tiles with TMA (cp.async.bulk.tensor); grids with Ny % 4 != 0 use plain loads."""
+    om = oracle_mod
+    lib = imhd._lib.load()
+    dims = (52, 44, 33)
+    g, d, Q0 = make_case(O, om, *dims, ic="bennett")
+    for path, D in paths(om):
+        a = run_fused(imhd, Q0, path, D, DT, d, 6)
+        lib.imhd_set_kernel_variant(1)
+        try:
+            b = run_fused(imhd, Q0, path, D, DT, d, 6)
+        finally:
+            lib.imhd_set_kernel_variant(0)
+        assert bits_equal(a, b), path
+
+
 def test_fused_matches_granular_on_device(imhd, torch, O, oracle_mod):
     """Two independent CUDA implementations of the same step agree to rounding."""
     om = oracle_mod
