@@ -704,14 +704,23 @@ static bool make_tile_map(CUtensorMap* map, const FusedArgs& A, int nplanes, int
 }
 
 static int pick_chunk(FusedArgs& A, int nz) {
-    // chunk length: enough chunks for several waves of blocks, long enough to amortise the 2 warm-up planes
+    // z-chunks: one block per SM is resident (register-limited), so the launch runs in waves of `sms` blocks.  Pick the
+    // chunk count that minimises  waves x (chunk length + warm-up)  -- i.e. fill the last wave -- with chunks long
+    // enough to amortise the two warm-up planes (each costs about half a plane).
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (long long)A.ntile_i * A.ntile_j;
-    int nchunk = (int)((8LL * sms + tiles - 1) / tiles);
-    int chunk = (nz + nchunk - 1) / nchunk;
-    if (chunk < 16) chunk = 16;
+    int best_n = 1;
+    double best = 1e300;
+    const int nmax = nz / 12 > 1 ? nz / 12 : 1;
+    for (int n = 1; n <= nmax; ++n) {
+        const int len = (nz + n - 1) / n;
+        const long long blocks = tiles * ((nz + len - 1) / len);
+        const double cost = (double)((blocks + sms - 1) / sms) * (len + 1.0);
+        if (cost < best * 0.999) { best = cost; best_n = n; }
+    }
+    int chunk = (nz + best_n - 1) / best_n;
     if (g_chunk_override > 0) chunk = g_chunk_override;
     if (chunk < 2) chunk = 2;
     if (chunk > nz) chunk = nz;
