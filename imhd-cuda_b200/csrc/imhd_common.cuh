@@ -33,6 +33,8 @@ inline Params make_params(int path, float D, float dt, float dx, float dy, float
     p.dc.cy = 1.0 / ((double)dy * (double)dy);
     p.dc.cz = 1.0 / ((double)dz * (double)dz);
     p.dc.cxf = (float)p.dc.cx; p.dc.cyf = (float)p.dc.cy; p.dc.czf = (float)p.dc.cz;
+    p.dc.c0f = (float)(-2.0 * (p.dc.cx + p.dc.cy + p.dc.cz));
+    p.dc.dtD = dt * D;
     return p;
 }
 

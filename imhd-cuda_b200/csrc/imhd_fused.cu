@@ -63,9 +63,7 @@ __device__ __forceinline__ void ldg8(const float* __restrict__ A, long long off,
     for (int v = 0; v < 8; ++v) U[v] = __ldg(A + off + v * vs);
 }
 
-__device__ __forceinline__ void hflux(const float U[8], float h[8]) {
-    flux_indexed<false, DIR_Z>(U, make_aux<false>(U), h);
-}
+__device__ __forceinline__ void hflux(const float U[8], float h[8]) { flux_idx<DIR_Z>(U, make_prim(U), h); }
 
 // -----------------------------------------------------------------------------------------------
 // Predictor at one cell from raw states (fast recipe).  c = Q(i,j,k), xp = Q(i+1,j,k),
@@ -77,14 +75,14 @@ __device__ __forceinline__ void qint_cell(const float c[8], const float xp[8], c
                                           const float hp[8], const float xm[8], const float ym[8], const float zm[8],
                                           const float zp[8], bool bottom, bool right, bool front, bool lap,
                                           const Params& P, float out[8]) {
-    const Aux<false> a = make_aux<false>(c);
+    const Prim s = make_prim(c);
     float f[8], g[8], t[8], dF[8], dG[8], dH[8];
-    flux_indexed<false, DIR_X>(c, a, f);
-    flux_indexed<false, DIR_Y>(c, a, g);
-    flux_indexed<false, DIR_X>(xp, make_aux<false>(xp), t);
+    flux_idx<DIR_X>(c, s, f);
+    flux_idx<DIR_Y>(c, s, g);
+    flux_idx<DIR_X>(xp, make_prim(xp), t);
 #pragma unroll
     for (int v = 0; v < 8; ++v) dF[v] = bottom ? -f[v] : t[v] - f[v];
-    flux_indexed<false, DIR_Y>(yp, make_aux<false>(yp), t);
+    flux_idx<DIR_Y>(yp, make_prim(yp), t);
 #pragma unroll
     for (int v = 0; v < 8; ++v) dG[v] = right ? -g[v] : t[v] - g[v];
 #pragma unroll
@@ -100,8 +98,10 @@ __device__ __forceinline__ void qint_cell(const float c[8], const float xp[8], c
         float base = c[v];
         if (v == MZ && bottom && right) base = c[MX];
         float r = fmaf(-P.tz, dH[v], fmaf(-P.ty, dG[v], fmaf(-P.tx, dF[v], base)));
-        if (PATH == IMHD_PATH_B && lap)
-            r = fmaf(P.dt, num_diff<false>(c[v], xp[v], yp[v], zp[v], xm[v], ym[v], zm[v], P.D, P.dc), r);
+        if (PATH == IMHD_PATH_B) {
+            const float rd = add_diffusion(r, c[v], xp[v], yp[v], zp[v], xm[v], ym[v], zm[v], P.dc);
+            r = lap ? rd : r;
+        }
         out[v] = r;
     }
 }
@@ -115,19 +115,25 @@ template <int PATH>
 __device__ __forceinline__ void corr_cell(const float q[8], const float c[8], const float xm[8], const float ym[8],
                                           const float zm[8], const float xp[8], const float yp[8], const float zp[8],
                                           const Params& P, float out[8]) {
-    const Aux<false> ac = make_aux<false>(c), ai = make_aux<false>(xm), aj = make_aux<false>(ym);
-    const float invk = fast_rcp(zm[RHO]);
-    const float KEk = h_KE<false>(zm[RHO], zm[MX], zm[MY], zm[MZ], invk);
-    const float Bk = h_Bsq<false>(xm[BX], ym[BY], zm[BZ]);                                        // B-4
-    const float pk = h_p<false>(zm[EN], Bk, KEk);
-    const float Dk = h_Bdotu<false>(zm[RHO], zm[MX], ym[MY], zm[MZ], zm[BX], zm[BY], zm[BZ], invk);  // B-5
+    const Prim sc = make_prim(c);
     float fc[8], gc[8], hc[8], fi[8], gj[8], hk[8];
-    flux_local<false, DIR_X>(c, ac.p, ac.Bsq, ac.Bdotu, ac.invf, fc);
-    flux_local<false, DIR_Y>(c, ac.p, ac.Bsq, ac.Bdotu, ac.invf, gc);
-    flux_local<false, DIR_Z>(c, ac.p, ac.Bsq, ac.Bdotu, ac.invf, hc);
-    flux_local<false, DIR_X>(xm, ai.p, ai.Bsq, ai.Bdotu, ai.invf, fi);
-    flux_local<false, DIR_Y>(ym, aj.p, aj.Bsq, aj.Bdotu, aj.invf, gj);
-    flux_local<false, DIR_Z>(zm, pk, Bk, Dk, invk, hk);
+    flux_loc<DIR_X>(c, sc, fc);
+    flux_loc<DIR_Y>(c, sc, gc);
+    flux_loc<DIR_Z>(c, sc, hc);
+    flux_loc<DIR_X>(xm, make_prim(xm), fi);
+    flux_loc<DIR_Y>(ym, make_prim(ym), gj);
+    {   // k-1 point with the reference's mixed neighbours: Bsq from (Bx(i-1), By(j-1), Bz(k-1)) (B-4), Bdotu with
+        // rhovy(j-1) (B-5); KE and the velocities from the k-1 state itself
+        Prim sk;
+        const float inv = fast_rcp(zm[RHO]);
+        sk.ux = zm[MX] * inv; sk.uy = zm[MY] * inv; sk.uz = zm[MZ] * inv;
+        sk.Bsq = fmaf(zm[BZ], zm[BZ], fmaf(ym[BY], ym[BY], xm[BX] * xm[BX]));
+        const float ke = fmaf(sk.uz, zm[MZ], fmaf(sk.uy, zm[MY], sk.ux * zm[MX]));
+        sk.p = kGm1f * fmaf(-0.5f, sk.Bsq, zm[EN] - ke);
+        sk.ptot = fmaf(0.5f, sk.Bsq, sk.p);
+        sk.Bdotu = fmaf(sk.uz, zm[BZ], fmaf(ym[MY] * inv, zm[BY], sk.ux * zm[BX]));
+        flux_loc<DIR_Z>(zm, sk, hk);
+    }
     if (PATH == IMHD_PATH_B) fi[RHO] = xm[RHO];  // B-6
     const float hx = 0.5f * P.tx, hy = 0.5f * P.ty, hz = 0.5f * P.tz;
 #pragma unroll
@@ -138,8 +144,7 @@ __device__ __forceinline__ void corr_cell(const float q[8], const float c[8], co
         const float s = q[v] + c[v];
         const float T = fmaf(hx, dF, fmaf(hy, dG, hz * dH));
         float r = fmaf(0.5f, s, -T);
-        if (PATH == IMHD_PATH_B)
-            r = fmaf(P.dt, num_diff<false>(c[v], xp[v], yp[v], zp[v], xm[v], ym[v], zm[v], P.D, P.dc), r);
+        if (PATH == IMHD_PATH_B) r = add_diffusion(r, c[v], xp[v], yp[v], zp[v], xm[v], ym[v], zm[v], P.dc);
         out[v] = r;
     }
 }

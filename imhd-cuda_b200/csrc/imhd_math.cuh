@@ -174,13 +174,97 @@ __device__ __forceinline__ void flux_local(const float U[8], float p, float Bsq,
 }
 
 // ------------------------------------------------------------------------------------------
+// FAST recipe, flux tensors from once-per-state primitives.  The two families differ only in the
+// induction and energy fluxes; momentum fluxes and the aliases F(my)=G(mx), F(mz)=H(mx),
+// G(mz)=H(my) (kernels_od_fluxes.cu:152-183) are shared.  ~19 ops per state + ~13 per direction.
+// ------------------------------------------------------------------------------------------
+struct Prim {
+    float ux, uy, uz;   // m / rho
+    float Bsq, p, ptot, Bdotu;
+};
+
+__device__ __forceinline__ Prim make_prim(const float U[8]) {
+    Prim s;
+    const float inv = fast_rcp(U[RHO]);
+    s.ux = U[MX] * inv; s.uy = U[MY] * inv; s.uz = U[MZ] * inv;
+    s.Bsq = fmaf(U[BZ], U[BZ], fmaf(U[BY], U[BY], U[BX] * U[BX]));
+    const float ke = fmaf(s.uz, U[MZ], fmaf(s.uy, U[MY], s.ux * U[MX]));   // (m.m)/rho, no 1/2 (B-1)
+    s.p = kGm1f * fmaf(-0.5f, s.Bsq, U[EN] - ke);
+    s.ptot = fmaf(0.5f, s.Bsq, s.p);
+    s.Bdotu = fmaf(s.uz, U[BZ], fmaf(s.uy, U[BY], s.ux * U[BX]));
+    return s;
+}
+
+// momentum part of the d-direction flux, common to both families
+template <int DIR>
+__device__ __forceinline__ void flux_mom(const float U[8], const Prim& s, float f[8]) {
+    const float ud = DIR == DIR_X ? s.ux : (DIR == DIR_Y ? s.uy : s.uz);
+    const float bd = U[BX + DIR];
+    f[RHO] = U[MX + DIR];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (c == DIR) {
+            f[MX + c] = fmaf(ud, U[MX + c], fmaf(-bd, bd, s.ptot));
+        } else {
+            // (m_lo/rho) * m_hi - B_lo*B_hi with lo < hi: one expression for both aliases
+            const int lo = c < DIR ? c : DIR, hi = c < DIR ? DIR : c;
+            const float ulo = lo == 0 ? s.ux : s.uy;
+            f[MX + c] = fmaf(ulo, U[MX + hi], -(U[BX + lo] * U[BX + hi]));
+        }
+    }
+    f[BX + DIR] = 0.0f;
+}
+
+// INDEXED family (predictor): induction with the undivided term (B-2), energy without parentheses (B-3)
+template <int DIR>
+__device__ __forceinline__ void flux_idx(const float U[8], const Prim& s, float f[8]) {
+    flux_mom<DIR>(U, s, f);
+    const float ud = DIR == DIR_X ? s.ux : (DIR == DIR_Y ? s.uy : s.uz);
+    const float md = U[MX + DIR], bd = U[BX + DIR];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (c == DIR) continue;
+        const float uc = c == 0 ? s.ux : (c == 1 ? s.uy : s.uz);
+        // c < DIR: (m_c/rho) B_d - B_c m_d ;  c > DIR: -( (m_d/rho) B_c - B_d m_c )
+        if (c < DIR) f[BX + c] = fmaf(uc, bd, -(U[BX + c] * md));
+        else         f[BX + c] = fmaf(bd, U[MX + c], -(ud * U[BX + c]));
+    }
+    f[EN] = fmaf(-s.Bdotu, bd, fmaf(s.Bsq, ud, U[EN] + s.p));
+}
+
+// LOCAL family (corrector): (m_c/rho) B_d - (m_d/rho) B_c ; (e + p + Bsq/2)(m_d/rho) - Bdotu B_d
+template <int DIR>
+__device__ __forceinline__ void flux_loc(const float U[8], const Prim& s, float f[8]) {
+    flux_mom<DIR>(U, s, f);
+    const float ud = DIR == DIR_X ? s.ux : (DIR == DIR_Y ? s.uy : s.uz);
+    const float bd = U[BX + DIR];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (c == DIR) continue;
+        const float uc = c == 0 ? s.ux : (c == 1 ? s.uy : s.uz);
+        f[BX + c] = fmaf(uc, bd, -(ud * U[BX + c]));
+    }
+    f[EN] = fmaf(U[EN] + s.ptot, ud, -(s.Bdotu * bd));
+}
+
+// ------------------------------------------------------------------------------------------
 // Diffusion stencil D * lap(q) (diffusion.cu:8-19); cx = 1/dx^2 etc. precomputed in fp64 on the
 // host exactly as `1.0 / pow(dx, 2)`.
 // ------------------------------------------------------------------------------------------
 struct DiffCoef {
     double cx, cy, cz;     // EXACT
     float cxf, cyf, czf;   // fast
+    float c0f;             // fast: -2 (cx + cy + cz)
+    float dtD;             // fast: dt * D
 };
+
+// fast: q + dt*D*lap folded into one chain: r + dtD * (cx (xp+xm) + cy (yp+ym) + cz (zp+zm) + c0 q).
+// The cancellation error of this form is ~1e-7 * (2/dx^2) * dt*D * |q| << ulp(q) for every grid of interest.
+__device__ __forceinline__ float add_diffusion(float r, float q, float xp, float yp, float zp, float xm, float ym, float zm,
+                                               const DiffCoef& c) {
+    const float lap = fmaf(c.cxf, xp + xm, fmaf(c.cyf, yp + ym, fmaf(c.czf, zp + zm, c.c0f * q)));
+    return fmaf(c.dtD, lap, r);
+}
 
 template <bool EXACT>
 __device__ __forceinline__ float num_diff(float q, float qip1, float qjp1, float qkp1, float qim1, float qjm1,
