@@ -63,6 +63,11 @@ SIGNATURES = {
     "imhd_ctx_device_state": (_p, [_p]),
     "imhd_ctx_stream": (_p, [_p]),
     "imhd_ctx_synchronize": (_i, [_p]),
+    "imhd_h5_write_fluidvars": (_i, [C.c_char_p, _p, _i, _i, _i, _i]),
+    "imhd_h5_write_grid": (_i, [C.c_char_p, _p, _p, _p, _i, _i, _i]),
+    "imhd_ctx_write_frame": (_i, [_p, C.c_char_p, _i]),
+    "imhd_ctx_flush_output": (_i, [_p]),
+    "imhd_ctx_write_grid": (_i, [_p, C.c_char_p]),
     "imhd_run_host": (_i, [_p, _p, _p, _i, _f, _f, _f, _f, _f, _i]),
 }
 

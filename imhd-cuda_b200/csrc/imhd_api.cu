@@ -3,9 +3,15 @@
 // src/on-device/no_diffusion.cu:284-337: no per-phase cudaDeviceSynchronize, no per-step
 // blocking D2H, one fused kernel per step on a single stream.
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <new>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "imhd_common.cuh"
 
@@ -47,6 +53,20 @@ struct imhd_ctx {
     int path;
     float D, dt, dx, dy, dz, corner_e;
     float bounds[6];
+    // ---- asynchronous output (replaces the per-step blocking cudaMemcpy + fork of main.cu:216-226) ----
+    float* snap;             // device snapshot of the frame being written out
+    float* pinned[2];        // pinned host staging, double buffered
+    cudaStream_t copy_stream;
+    cudaEvent_t snap_done, copy_done[2];
+    int next_slot;
+    struct Job { int slot, frame, attrs; std::string path; };
+    std::deque<Job>* jobs;
+    std::mutex* mu;
+    std::condition_variable* cv;
+    std::thread* writer;
+    bool slot_busy[2];
+    bool stop;
+    int write_errors;
 };
 
 extern "C" int imhd_abi_version(void) { return 1; }
@@ -89,6 +109,16 @@ extern "C" void imhd_destroy(imhd_ctx* c) {
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     cudaFree(c->buf[0]); cudaFree(c->buf[1]);
     cudaFree(c->gx); cudaFree(c->gy); cudaFree(c->gz); cudaFree(c->qint_planes);
+    if (c->writer) {
+        { std::lock_guard<std::mutex> g(*c->mu); c->stop = true; }
+        c->cv->notify_all();
+        c->writer->join();
+        delete c->writer; delete c->jobs; delete c->mu; delete c->cv;
+        cudaFree(c->snap);
+        for (int s = 0; s < 2; ++s) { cudaFreeHost(c->pinned[s]); cudaEventDestroy(c->copy_done[s]); }
+        cudaEventDestroy(c->snap_done);
+        cudaStreamDestroy(c->copy_stream);
+    }
     delete c;
 }
 
@@ -246,4 +276,96 @@ extern "C" int imhd_run_host(imhd_ctx* c, const float* host_Q_in, float* host_Q_
     if (int e = imhd_ctx_prime(c, path, D, dt)) return e;
     if (int e = imhd_ctx_step(c, nsteps)) return e;
     return imhd_ctx_get_state(c, host_Q_out);
+}
+
+// ---- output: fluidvars_<frame>.h5 / grid.h5 -----------------------------------------------
+extern "C" int imhd_h5_write_fluidvars(const char*, const float*, int, int, int, int);
+extern "C" int imhd_h5_write_grid(const char*, const float*, const float*, const float*, int, int, int);
+
+static void writer_main(imhd_ctx* c) {
+    cudaSetDevice(c->device);
+    for (;;) {
+        imhd_ctx::Job job;
+        {
+            std::unique_lock<std::mutex> lk(*c->mu);
+            c->cv->wait(lk, [&] { return c->stop || !c->jobs->empty(); });
+            if (c->jobs->empty()) return;
+            job = c->jobs->front();
+            c->jobs->pop_front();
+        }
+        cudaEventSynchronize(c->copy_done[job.slot]);
+        const int rc = imhd_h5_write_fluidvars(job.path.c_str(), c->pinned[job.slot], c->Nx, c->Ny, c->Nz, job.attrs);
+        {
+            std::lock_guard<std::mutex> g(*c->mu);
+            if (rc) ++c->write_errors;
+            c->slot_busy[job.slot] = false;
+        }
+        c->cv->notify_all();
+    }
+}
+
+static int start_writer(imhd_ctx* c) {
+    if (c->writer) return 0;
+    const size_t bytes = 8 * c->cells * sizeof(float);
+    IMHD_CUDA(cudaMalloc(&c->snap, bytes));
+    for (int s = 0; s < 2; ++s) {
+        IMHD_CUDA(cudaMallocHost(&c->pinned[s], bytes));
+        IMHD_CUDA(cudaEventCreateWithFlags(&c->copy_done[s], cudaEventDisableTiming));
+    }
+    IMHD_CUDA(cudaEventCreateWithFlags(&c->snap_done, cudaEventDisableTiming));
+    IMHD_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    c->jobs = new std::deque<imhd_ctx::Job>();
+    c->mu = new std::mutex();
+    c->cv = new std::condition_variable();
+    c->writer = new std::thread(writer_main, c);
+    return 0;
+}
+
+// Queue frame `frame` of the current state for output as <dir>fluidvars_<frame>.h5 (attributes on frame 0 only, as
+// main.cu:141-145).  Returns at once: a device-side snapshot (1 copy at HBM speed) decouples the time loop from the
+// D2H copy and the file write, which run on a copy stream and a writer thread.
+extern "C" int imhd_ctx_write_frame(imhd_ctx* c, const char* dir, int frame) {
+    CTX_CHECK(c);
+    if (!dir) { set_error("imhd_ctx_write_frame: null directory"); return IMHD_E_INVALID; }
+    if (int e = start_writer(c)) return e;
+    const int slot = c->next_slot;
+    {   // wait until the staging slot's previous frame is on disk (back-pressure: at most 2 frames in flight)
+        std::unique_lock<std::mutex> lk(*c->mu);
+        c->cv->wait(lk, [&] { return !c->slot_busy[slot]; });
+        c->slot_busy[slot] = true;
+    }
+    const size_t bytes = 8 * c->cells * sizeof(float);
+    IMHD_CUDA(cudaStreamWaitEvent(c->stream, c->copy_done[slot], 0));  // snapshot buffer free again?
+    IMHD_CUDA(cudaMemcpyAsync(c->snap, c->buf[c->cur], bytes, cudaMemcpyDeviceToDevice, c->stream));
+    IMHD_CUDA(cudaEventRecord(c->snap_done, c->stream));
+    IMHD_CUDA(cudaStreamWaitEvent(c->copy_stream, c->snap_done, 0));
+    IMHD_CUDA(cudaMemcpyAsync(c->pinned[slot], c->snap, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    IMHD_CUDA(cudaEventRecord(c->copy_done[slot], c->copy_stream));
+    // the NEXT snapshot must not overwrite `snap` before this D2H has drained it
+    IMHD_CUDA(cudaStreamWaitEvent(c->stream, c->copy_done[slot], 0));
+    {
+        std::lock_guard<std::mutex> g(*c->mu);
+        c->jobs->push_back({slot, frame, frame == 0 ? 1 : 0, std::string(dir) + "fluidvars_" + std::to_string(frame) + ".h5"});
+    }
+    c->cv->notify_all();
+    c->next_slot = 1 - slot;
+    return 0;
+}
+
+// Block until every queued frame is on disk; returns IMHD_E_IO if any write failed.
+extern "C" int imhd_ctx_flush_output(imhd_ctx* c) {
+    CTX_CHECK(c);
+    if (!c->writer) return 0;
+    std::unique_lock<std::mutex> lk(*c->mu);
+    c->cv->wait(lk, [&] { return c->jobs->empty() && !c->slot_busy[0] && !c->slot_busy[1]; });
+    if (c->write_errors) { set_error("%d frame(s) could not be written", c->write_errors); return IMHD_E_IO; }
+    return 0;
+}
+
+extern "C" int imhd_ctx_write_grid(imhd_ctx* c, const char* dir) {
+    CTX_CHECK(c);
+    if (int e = need_grids(c)) return e;
+    std::vector<float> x(c->Nx), y(c->Ny), z(c->Nz);
+    if (int e = imhd_ctx_get_grids(c, x.data(), y.data(), z.data())) return e;
+    return imhd_h5_write_grid((std::string(dir) + "grid.h5").c_str(), x.data(), y.data(), z.data(), c->Nx, c->Ny, c->Nz);
 }

@@ -164,6 +164,20 @@ float* imhd_ctx_device_state(imhd_ctx* ctx);
 void* imhd_ctx_stream(imhd_ctx* ctx);
 int imhd_ctx_synchronize(imhd_ctx* ctx);
 
+/* ---- output: the reference's on-disk contract without libhdf5 -----------------
+ * fluidvars_<it>.h5: 8 one-dimensional fp32 datasets rho, rhovx, rhovy, rhovz, Bx, By, Bz, e of Nx*Ny*Nz
+ * elements in IDX3D order (src/on-device/utils/phdf5_write_all.cpp:87-169); with_attributes adds
+ * cubeDimensions / cubeDimensionsNames / storagePattern (hdf5_write_attributes.cpp:55-98, frame 0 only).
+ * grid.h5: x_grid, y_grid, z_grid with scalar attributes spacing, dimension (hdf5_write_grid.cpp:78-137). */
+int imhd_h5_write_fluidvars(const char* path, const float* host_Q, int Nx, int Ny, int Nz, int with_attributes);
+int imhd_h5_write_grid(const char* path, const float* x, const float* y, const float* z, int Nx, int Ny, int Nz);
+/* Queue the current state as <dir>fluidvars_<frame>.h5 (dir ends with '/'); returns at once -- device
+ * snapshot, D2H on a copy stream, file write on a writer thread (replaces main.cu:216-226).  At most
+ * two frames are in flight. */
+int imhd_ctx_write_frame(imhd_ctx* ctx, const char* dir, int frame);
+int imhd_ctx_flush_output(imhd_ctx* ctx);
+int imhd_ctx_write_grid(imhd_ctx* ctx, const char* dir);
+
 /* Whole job through HOST buffers (the e2e path bench.py times): upload host_Q_in, prime,
  * run nsteps fused steps, download into host_Q_out.  Both buffers 8*Nx*Ny*Nz floats. */
 int imhd_run_host(imhd_ctx* ctx, const float* host_Q_in, float* host_Q_out, int path, float D,

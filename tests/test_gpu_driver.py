@@ -1,0 +1,74 @@
+"""End-to-end drop-in test (GPU): the launcher + imhd-cuda / imhd-cuda_nodiff executables with the reference's
+argv lists, reading back the .h5 frames they write and comparing with the CPU oracle."""
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import BOUNDS, ROOT, make_case
+from h5_min_reader import Reader
+
+pytestmark = pytest.mark.gpu
+VARS = ("rho", "rhovx", "rhovy", "rhovz", "Bx", "By", "Bz", "e")
+DRV = os.path.join(ROOT, "imhd-cuda_b200", "driver")
+
+
+def read_frame(path, dims):
+    Nx, Ny, Nz = dims
+    r = Reader(path)
+    return np.stack([r.dataset(v)[0].reshape(Nz, Nx, Ny) for v in VARS])
+
+
+def patched_input(tmp_path, src, **over):
+    lines = []
+    for line in open(os.path.join(DRV, src)):
+        k, v = line.strip().split("=", 1)
+        lines.append(f"{k}={over.get(k, v)}")
+    p = tmp_path / src
+    p.write_text("\n".join(lines) + "\n")
+    return str(p)
+
+
+@pytest.mark.parametrize("mode", ["nodiff", "diffusion"])
+def test_launcher_runs_the_drop_in_driver(tmp_path, O, oracle_mod, mode):
+    om = oracle_mod
+    dims = (32, 28, 20)
+    Nx, Ny, Nz = dims
+    nt = 13
+    data = str(tmp_path / "data") + "/"
+    inp = patched_input(tmp_path, "input.inp" if mode == "nodiff" else "input_diffusion.inp", Nt=nt, Nx=Nx, Ny=Ny, Nz=Nz)
+    env = dict(os.environ, IMHD_OUTPUT_EVERY="4")
+    os.makedirs(data)
+    open(data + "stale.h5", "w").write("x")      # the launcher wipes the data directory first
+    open(data + "README.md", "w").write("keep")  # ... except README.md
+    out = subprocess.run([sys.executable, os.path.join(DRV, "simulation_launcher.py"), mode, "--input", inp, "--data-dir", data],
+                         capture_output=True, text=True, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    files = sorted(os.listdir(data))
+    assert "stale.h5" not in files and "README.md" in files and "grid.h5" in files
+    frames = sorted(int(f[len("fluidvars_"):-3]) for f in files if f.startswith("fluidvars_"))
+    assert frames == [0, 4, 8, 12], frames   # it % 4 == 0 and the last step Nt-1
+    # grid.h5
+    g = Reader(data + "grid.h5")
+    go = O.init_grids(BOUNDS, *dims)
+    for name, ref in zip(("x_grid", "y_grid", "z_grid"), go):
+        arr, attrs = g.dataset(name)
+        assert np.array_equal(arr, ref) and attrs["dimension"] == len(ref)
+    # frame 0 = initial condition (+ attributes); last frame = Nt-1 steps of the reference pipeline
+    ic = "bennett" if mode == "nodiff" else "screwpinch"
+    path, D = (om.PATH_A, 0.0) if mode == "nodiff" else (om.PATH_B, 0.01)
+    _, d, Q0 = make_case(O, om, *dims, ic=ic)
+    r0 = Reader(data + "fluidvars_0.h5")
+    assert r0.dataset("rho")[1]["cubeDimensionsNames"] == ["Nx", "Ny", "Nz"]
+    assert Reader(data + "fluidvars_4.h5").dataset("rho")[1] == {}
+    qo, io = Q0.copy(), np.zeros_like(Q0)
+    om_dt = 1e-4
+    O.prime(qo, io, path, D, om_dt, *d)
+    f0 = read_frame(data + "fluidvars_0.h5", dims)
+    np.testing.assert_allclose(f0, qo, rtol=0, atol=5e-7)   # path A: after the initial wall/PBC pass; GPU logf/cosf within 2 ulp
+    O.steps(qo, io, path, nt - 1, D, om_dt, *d)
+    fl = read_frame(data + f"fluidvars_{nt - 1}.h5", dims)
+    assert (om.normalised_linf(fl, qo) <= 1e-5).all()
