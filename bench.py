@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NX, NY, NZ_PER_GPU = 304, 304, 592
+STRONG = (1024, 1024, 2048)  # BASELINE.json configs[3]: total work fixed, split across 2/4/8 GPUs (--workload strong)
 BOUNDS = (-3.14159, 3.14159) * 3
 J0, D, DT = 1.0, 0.01, 1e-4
 BYTES_PER_CELL_UPDATE = 64  # 8 fp32 read + 8 fp32 written
@@ -156,6 +157,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): 304x304x592 per GPU; strong: 1024x1024x2048 in total (needs >= 2 GPUs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (the strong workload pins 34 GB per rank at N=2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -185,6 +189,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         comm = slabmod.TorchComm()
 
+    global NX, NY, NZ_PER_GPU
+    if args.workload == "strong":
+        if world < 2:
+            raise SystemExit("--workload strong: 1024x1024x2048 needs 2 x 64 GiB of state, run it on >= 2 GPUs")
+        NX, NY = STRONG[0], STRONG[1]
+        NZ_PER_GPU = STRONG[2] // world
     nz_global = NZ_PER_GPU * world
     dx, dy, dz = spacing(nz_global)
     solver = slabmod.SlabSolver(NX, NY, nz_global, pkg.PATH_B, D, DT, dx, dy, dz, comm=comm, corner_e=0.0)
@@ -244,7 +254,10 @@ def main():
 
     # ---- end to end through host buffers (`e2e`): pinned host state -> device, K steps, result back to the host -----
     slab_bytes = 8 * cells_local * 4
-    if world == 1:
+    e2e_s = None
+    if args.no_e2e:
+        pass
+    elif world == 1:
         host_in = torch.empty((8, L.nzl, NX, NY), dtype=torch.float32, pin_memory=True)
         host_out = torch.empty_like(host_in, pin_memory=True)
         reset_state()
@@ -274,7 +287,7 @@ def main():
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = t.item()
-    e2e = {"value": cells_global * args.steps / e2e_s / 1e9, "unit": "GLUPS",
+    e2e = None if e2e_s is None else {"value": cells_global * args.steps / e2e_s / 1e9, "unit": "GLUPS",
            "h2d_bytes_per_step": slab_bytes * world / args.steps, "d2h_bytes_per_step": slab_bytes * world / args.steps,
            "note": f"one C-ABI job: pinned host state -> device, {args.steps} fused steps, state -> host; copies inside the timed region"}
 
@@ -283,7 +296,7 @@ def main():
         achieved = BYTES_PER_CELL_UPDATE * cells_local / (fused_ms * 1e-3) / 1e9
         line = {
             "metric": "cell_updates_per_sec", "value": value, "unit": "GLUPS", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.workload,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "finite": finite,
             "roofline": {"bound": "hbm", "kernel": "k_fused_step<PATH_B,16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
