@@ -44,6 +44,7 @@ SIGNATURES = {
     "imhd_init_screwpinch_stride": (_i, [_p, _f, _p, _p, _p] + _dims + [_p]),
     "imhd_init_cubic_bennett_vortex_m0": (_i, [_p, _f, _f, _p, _p, _p] + _dims + [_p]),
     "imhd_step_fused": (_i, [_p, _p, _p, _p, _p, C.POINTER(Slab), _p]),
+    "imhd_step_fused_planes": (_i, [_p, _p, _p, _p, _p, C.POINTER(Slab), _i, _i, _p]),
     "imhd_wall_energy_fixed_point": (_f, [_f, _i]),
     "imhd_set_chunk": (None, [_i]),
     "imhd_set_kernel_variant": (None, [_i]),

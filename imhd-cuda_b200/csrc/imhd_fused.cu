@@ -42,7 +42,8 @@ struct FusedArgs {
     int kbase;          // global plane index held by array plane 0
     int kmin, kmax;     // global planes that may be READ from Qin: [kmin, kmax]
     int k0, k1;         // owned (written) global planes [k0, k1)
-    int ka0, kb0;       // planes the marching kernel writes: [max(k0,1), min(k1, A: Nz / B: Nz-1))
+    int ka0, kb0;       // planes the marching kernel owns: [max(k0,1), min(k1, A: Nz / B: Nz-1))
+    int kfrom, kto;     // planes THIS launch writes, a sub-range of [ka0, kb0) (comm/compute overlap launches the slab ends first)
     const float* qlo;   // (8,Nx,Ny) Qint at global plane ka0-1  (own Qint(0) when k0 == 0)
     const float* qhi;   // (8,Nx,Ny) Qint at global plane hi_plane = min(k1, Nz-1)
     const float* qwrap; // (8,Nx,Ny) Qint(Nz-2) == Qint(-1): path B, slab with k0 == 0 only (k=0 face)
@@ -208,8 +209,8 @@ __global__ void __launch_bounds__(TI * 32, 1) k_fused_step_ldg(const FusedArgs A
     const int tim = max(ti - 1, 0), tip = min(ti + 1, TI - 1);
     const int so = ti * 32 + lane, som = tim * 32 + lane, sop = tip * 32 + lane;  // smem slots: own, i-1, i+1
 
-    const int ka = A.ka0 + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kb0);
-    const bool first = blockIdx.z == 0;
+    const int ka = A.kfrom + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kto);
+    const bool first = ka == A.ka0;  // the plane below is the slab's qint_lo; otherwise re-derive it in a warm-up plane
     const int ks = first ? ka - 1 : ka - 2;
 
     auto plane_ptr = [&](int k) -> const float* {
@@ -444,8 +445,8 @@ __global__ void __launch_bounds__(TI * 32, 1) k_fused_step_tma(const FusedArgs A
     T.sop = min(ti + 1, TI - 1) * 32 + lane;
     T.lcol = (long long)min(i, P.Nx - 1) * P.Ny + min(j, P.Ny - 1);
 
-    const int ka = A.ka0 + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kb0);
-    const bool first = blockIdx.z == 0;
+    const int ka = A.kfrom + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kto);
+    const bool first = ka == A.ka0;  // the plane below is the slab's qint_lo; otherwise re-derive it in a warm-up plane
     const int ks = first ? ka - 1 : ka - 2;
     const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
     const int klast = kb + 1;  // last plane any iteration reads
@@ -642,6 +643,7 @@ static int fill_args(FusedArgs& A, const float* Qin, float* Qout, const float* q
     A.k0 = s->k0; A.k1 = s->k0 + s->nzl;
     A.ka0 = max(A.k0, 1);
     A.kb0 = min(A.k1, s->path == IMHD_PATH_A ? s->Nz : s->Nz - 1);
+    A.kfrom = A.ka0; A.kto = A.kb0;
     A.qlo = qlo; A.qhi = qhi; A.qwrap = qwrap;
     A.hi_plane = min(A.k1, s->Nz - 1);
     A.corner_e = s->corner_e;
@@ -708,6 +710,19 @@ static bool make_tile_map(CUtensorMap* map, const FusedArgs& A, int nplanes, int
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// cudaFuncSetAttribute is per device: remember which devices already have the opt-in shared-memory size set
+template <class K>
+static int ensure_smem(K kernel, size_t bytes, unsigned long long& done_mask) {
+    int dev = 0;
+    IMHD_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(done_mask & bit)) {
+        IMHD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        done_mask |= bit;
+    }
+    return 0;
+}
+
 static int pick_chunk(FusedArgs& A, int nz) {
     // z-chunks: one block per SM is resident (register-limited), so the launch runs in waves of `sms` blocks.  Pick the
     // chunk count that minimises  waves x (chunk length + warm-up)  -- i.e. fill the last wave -- with chunks long
@@ -736,7 +751,7 @@ static int pick_chunk(FusedArgs& A, int nz) {
 template <int PATH, int TI>
 static int launch_fused(FusedArgs& A, int nplanes_array, cudaStream_t st) {
     const Params& P = A.P;
-    const int nz = A.kb0 - A.ka0;
+    const int nz = A.kto - A.kfrom;
     if (nz <= 0) return 0;
     // cells the corrector updates, counted from index 1: i in [1, Nx-1] (A) / [1, Nx-2] (B); edge cells ride along
     const int ni = PATH == IMHD_PATH_A ? P.Nx - 1 : P.Nx - 2, nj = PATH == IMHD_PATH_A ? P.Ny - 1 : P.Ny - 2;
@@ -746,11 +761,8 @@ static int launch_fused(FusedArgs& A, int nplanes_array, cudaStream_t st) {
         A.ntile_i = (ni + G::WI - 1) / G::WI;
         A.ntile_j = (nj + G::WJ - 1) / G::WJ;
         const int nchunk = pick_chunk(A, nz);
-        static bool attr_set = false;
-        if (!attr_set) {
-            IMHD_CUDA(cudaFuncSetAttribute(k_fused_step_tma<PATH, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-            attr_set = true;
-        }
+        static unsigned long long done = 0;
+        if (int e = ensure_smem(k_fused_step_tma<PATH, TI>, G::SMEM, done)) return e;
         k_fused_step_tma<PATH, TI><<<dim3(A.ntile_j, A.ntile_i, nchunk), dim3(32, TI), G::SMEM, st>>>(A, tmap);
         IMHD_LAUNCH_CHECK(1);
         return 0;
@@ -761,20 +773,24 @@ static int launch_fused(FusedArgs& A, int nplanes_array, cudaStream_t st) {
     A.ntile_j = (nj + WJ - 1) / WJ;
     const int nchunk = pick_chunk(A, nz);
     const size_t smem = 2 * 2 * 8 * TI * 32 * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        IMHD_CUDA(cudaFuncSetAttribute(k_fused_step_ldg<PATH, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static unsigned long long done = 0;
+    if (int e = ensure_smem(k_fused_step_ldg<PATH, TI>, smem, done)) return e;
     k_fused_step_ldg<PATH, TI><<<dim3(A.ntile_j, A.ntile_i, nchunk), dim3(32, TI), smem, st>>>(A);
     IMHD_LAUNCH_CHECK(1);
     return 0;
 }
 
-extern "C" int imhd_step_fused(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
-                               const float* qint_wrap, const imhd_slab* s, void* stream) {
+// Output planes [kfrom, kto) of the slab only (global indices, clipped to the owned range).  Any split of the owned
+// range into such calls writes the same bits as one imhd_step_fused call; the slab solver launches the planes next
+// to the slab ends first so their exchange overlaps the interior launch.
+extern "C" int imhd_step_fused_planes(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
+                                      const float* qint_wrap, const imhd_slab* s, int kfrom, int kto, void* stream) {
     FusedArgs A;
     if (int e = fill_args(A, Qin, Qout, qint_lo, qint_hi, qint_wrap, s)) return e;
+    kfrom = max(kfrom, A.k0); kto = min(kto, A.k1);
+    if (kfrom >= kto) return 0;
+    A.kfrom = max(kfrom, A.ka0); A.kto = min(kto, A.kb0);
+    const bool do_front = kfrom == 0, do_back = kto == s->Nz;
     if (Qin == Qout) { set_error("imhd_step_fused: Qin and Qout must be distinct buffers"); return IMHD_E_INVALID; }
     if (!qint_lo || !qint_hi || (s->path == IMHD_PATH_B && s->k0 == 0 && !qint_wrap)) {
         set_error("imhd_step_fused: missing predictor plane (qint_lo=%p qint_hi=%p qint_wrap=%p)", (const void*)qint_lo,
@@ -786,7 +802,7 @@ extern "C" int imhd_step_fused(const float* Qin, float* Qout, const float* qint_
     const unsigned pb = (unsigned)((P.plane + 255) / 256);
     if (s->path == IMHD_PATH_A) {
         if (int e = launch_fused<IMHD_PATH_A, 16>(A, s->nzl + 2 * (s->ghosts ? 1 : 0), st)) return e;
-        if (A.k0 == 0 && A.k1 == P.Nz) {  // PBCs on one GPU; across slabs the ghost exchange carries this plane
+        if (A.k0 == 0 && A.k1 == P.Nz && do_back) {  // PBCs on one GPU; across slabs the ghost exchange carries this plane
             k_plane_copy<<<pb, 256, 0, st>>>(Qout, (long long)(0 - A.kbase) * P.plane, (long long)(P.Nz - 1 - A.kbase) * P.plane,
                                              P.plane, A.vs);
             IMHD_LAUNCH_CHECK(1);
@@ -794,13 +810,19 @@ extern "C" int imhd_step_fused(const float* Qin, float* Qout, const float* qint_
         return 0;
     }
     if (int e = launch_fused<IMHD_PATH_B, 16>(A, s->nzl + 2 * (s->ghosts ? 1 : 0), st)) return e;
-    if (A.k0 == 0) {
+    if (do_front) {
         k_front_plane_B<<<dim3((P.Ny + 31) / 32, (P.Nx + 7) / 8), dim3(32, 8), 0, st>>>(A);
         IMHD_LAUNCH_CHECK(1);
     }
-    if (A.k1 == P.Nz) {
+    if (do_back) {
         k_back_plane_B<<<pb, 256, 0, st>>>(A);
         IMHD_LAUNCH_CHECK(1);
     }
     return 0;
+}
+
+extern "C" int imhd_step_fused(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
+                               const float* qint_wrap, const imhd_slab* s, void* stream) {
+    if (!s) { set_error("null slab descriptor"); return IMHD_E_INVALID; }
+    return imhd_step_fused_planes(Qin, Qout, qint_lo, qint_hi, qint_wrap, s, s->k0, s->k0 + s->nzl, stream);
 }

@@ -122,6 +122,14 @@ def step_fused(Qin, Qout, qint_lo, qint_hi, qint_wrap, slab: Slab):
                             _stream()))
 
 
+def step_fused_planes(Qin, Qout, qint_lo, qint_hi, qint_wrap, slab: Slab, kfrom: int, kto: int):
+    """Output planes [kfrom, kto) of the slab only (same bits as the full step for any split)."""
+    L = _lib.load()
+    wrap = _dev(qint_wrap) if qint_wrap is not None else None
+    check(L.imhd_step_fused_planes(_dev(Qin), _dev(Qout, Qin.shape), _dev(qint_lo), _dev(qint_hi), wrap, C.byref(slab),
+                                   kfrom, kto, _stream()))
+
+
 def wall_energy_fixed_point(e: float, max_iter: int) -> float:
     return float(_lib.load().imhd_wall_energy_fixed_point(e, max_iter))
 

@@ -9,10 +9,12 @@ Per time step and rank (ring neighbours, periodic in z):
        up-going   Qint(k1-1)   -> rank r+1's ``qint_lo``   (the last rank sends Qint(Nz-2) == Qint(-1), which
                                   rank 0 uses as ``qint_wrap`` for the k=0 face; rank 0's ``qint_lo`` is its own Qint(0))
        down-going Qint(k0)     -> rank r-1's ``qint_hi``   (rank 0 sends Qint(0): Qint(Nz-1) == Qint(0))
-  2. one fused kernel over the owned planes (``imhd_step_fused``)
+  2. the fused kernel over the owned planes (``imhd_step_fused_planes``: slab ends first, then the interior)
   3. exchange the new boundary planes of Q into the neighbours' ghost planes; for path A the plane the
      last rank sends up is the periodic copy Q[.,.,0] <- Q[.,.,Nz-1] (lib/on-device/kernels_fluidbcs.cu:498-510)
      and lands in rank 0's OWNED plane 0.
+Steps 1 and 3 run on a side stream underneath the interior launch of step 2 (the predictor planes of the next
+step only need the new end planes), so the interior never waits for a message.
 No reduction is needed anywhere (the reference has no global dt control).  Results are bit-identical for
 every number of ranks: each value is computed by the same device function from the same inputs.
 
@@ -98,7 +100,13 @@ class TorchComm:
 
 
 class SlabSolver:
-    """Time loop of one slab.  ``compute`` supplies qint_plane / step_fused (the C ABI through ops.py on a GPU)."""
+    """Time loop of one slab.  ``compute`` supplies qint_plane / step_fused_planes (the C ABI through ops.py on a GPU).
+
+    With more than one rank on GPUs the step is software-pipelined: the planes next to the slab ends are computed
+    first, then -- on a side stream, under the interior launch -- their ghost exchange, the two predictor planes of
+    the NEW state and the exchange of those.  The interior never waits for a message."""
+
+    EDGE = 8  # planes computed ahead at each slab end (>= 3: the predictor planes of the new state need them)
 
     def __init__(self, Nx, Ny, Nz, path, D, dt, dx, dy, dz, comm=None, compute=None, device="cuda", corner_e=0.0):
         import torch
@@ -119,10 +127,17 @@ class SlabSolver:
         self.Q = [torch.zeros(shape, dtype=torch.float32, device=device) for _ in range(2)]
         self.cur = 0
         pl = (8, Nx, Ny)
-        self.qint_lo, self.qint_hi, self.send_up, self.send_down, self.recv_lo, self.recv_hi = (
-            torch.zeros(pl, dtype=torch.float32, device=device) for _ in range(6))
+        mk = lambda: torch.zeros(pl, dtype=torch.float32, device=device)  # noqa: E731
+        # predictor planes are double buffered: the set for step n+1 is produced while step n still reads its own
+        self.qsets = [{"lo": mk(), "hi": mk(), "up": mk(), "down": mk()} for _ in range(2)]
+        self.qcur, self.q_ready = 0, False
+        self.send_up, self.send_down, self.recv_lo, self.recv_hi = mk(), mk(), mk(), mk()
         self.slab = compute.make_slab(Nx, Ny, Nz, path, D, dt, dx, dy, dz, k0=L.k0, nzl=L.nzl, ghosts=1,
                                       corner_e=corner_e)
+        self.overlap = world > 1 and str(device).startswith("cuda") and L.nzl >= 2 * self.EDGE + 2
+        if self.overlap:
+            self.side = torch.cuda.Stream()
+            self.ev_edges, self.ev_comm = torch.cuda.Event(), torch.cuda.Event()
 
     # ---- state in / out ----------------------------------------------------------------------------
     @property
@@ -136,32 +151,31 @@ class SlabSolver:
         src = t.as_tensor(Qglobal)
         lo, hi = max(L.k0 - 1, 0), min(L.k1 + 1, self.Nz)
         self.Q[self.cur][:, lo - L.k0 + 1: hi - L.k0 + 1].copy_(src[:, lo:hi])
+        self.q_ready = False
 
     # ---- exchanges -----------------------------------------------------------------------------------
-    def exchange_qint(self):
+    def exchange_qint(self, Q, qs):
+        """Fill the predictor-plane set `qs` for a step that starts from state array Q; returns (lo, hi, wrap)."""
         L, c = self.layout, self.compute
-        Q = self.Q[self.cur]
         if self.comm is None or L.world == 1:
-            c.qint_plane(Q, 0, self.slab, out=self.qint_hi)          # Qint(0) == Qint(Nz-1)
-            self.lo, self.hi, self.wrap = self.qint_hi, self.qint_hi, None
+            c.qint_plane(Q, 0, self.slab, out=qs["hi"])          # Qint(0) == Qint(Nz-1)
+            wrap = None
             if self.path == PATH_B:
-                c.qint_plane(Q, self.Nz - 2, self.slab, out=self.qint_lo)  # Qint(Nz-2) == Qint(-1)
-                self.wrap = self.qint_lo
-            return
-        c.qint_plane(Q, L.up_plane, self.slab, out=self.send_up)
-        c.qint_plane(Q, L.down_plane, self.slab, out=self.send_down)
-        self.comm.ring_exchange(self.send_up, self.send_down, self.qint_lo, self.qint_hi, L.up, L.down)
+                c.qint_plane(Q, self.Nz - 2, self.slab, out=qs["lo"])  # Qint(Nz-2) == Qint(-1)
+                wrap = qs["lo"]
+            return qs["hi"], qs["hi"], wrap
+        c.qint_plane(Q, L.up_plane, self.slab, out=qs["up"])
+        c.qint_plane(Q, L.down_plane, self.slab, out=qs["down"])
+        self.comm.ring_exchange(qs["up"], qs["down"], qs["lo"], qs["hi"], L.up, L.down)
         if L.rank == 0:  # received Qint(Nz-2) from the last rank; the plane below plane 1 is this rank's own Qint(0)
-            self.lo, self.hi, self.wrap = self.send_down, self.qint_hi, self.qint_lo
-        else:
-            self.lo, self.hi, self.wrap = self.qint_lo, self.qint_hi, None
+            return qs["down"], qs["hi"], qs["lo"]
+        return qs["lo"], qs["hi"], None
 
-    def exchange_ghosts(self):
+    def exchange_ghosts(self, Q):
         """New boundary planes of Q -> neighbours' ghost planes (+ the path A periodic copy)."""
         L = self.layout
-        Q = self.Q[self.cur]
         if self.comm is None or L.world == 1:
-            return  # the fused kernel wrote plane 0 itself (path A) and nothing reads a ghost plane
+            return  # the fused step wrote plane 0 itself (path A) and nothing reads a ghost plane
         self.send_up.copy_(Q[:, L.nzl])   # owned top plane k1-1
         self.send_down.copy_(Q[:, 1])     # owned bottom plane k0
         self.comm.ring_exchange(self.send_up, self.send_down, self.recv_lo, self.recv_hi, L.up, L.down)
@@ -174,12 +188,33 @@ class SlabSolver:
 
     # ---- time loop --------------------------------------------------------------------------------------
     def step(self, nsteps=1):
+        L, c, t = self.layout, self.compute, self.torch
         for _ in range(nsteps):
-            self.exchange_qint()
             Qin, Qout = self.Q[self.cur], self.Q[1 - self.cur]
-            self.compute.step_fused(Qin, Qout, self.lo, self.hi, self.wrap, self.slab)
+            if not self.q_ready:
+                self.planes = self.exchange_qint(Qin, self.qsets[self.qcur])
+                self.q_ready = True
+            lo, hi, wrap = self.planes
+            if not self.overlap:
+                c.step_fused_planes(Qin, Qout, lo, hi, wrap, self.slab, L.k0, L.k1)
+                self.cur = 1 - self.cur
+                self.exchange_ghosts(Qout)
+                self.q_ready = False
+                continue
+            E = self.EDGE
+            main = t.cuda.current_stream()
+            c.step_fused_planes(Qin, Qout, lo, hi, wrap, self.slab, L.k0, L.k0 + E)
+            c.step_fused_planes(Qin, Qout, lo, hi, wrap, self.slab, L.k1 - E, L.k1)
+            self.ev_edges.record(main)
+            c.step_fused_planes(Qin, Qout, lo, hi, wrap, self.slab, L.k0 + E, L.k1 - E)
+            with t.cuda.stream(self.side):   # under the interior launch: halo of the new state, predictor planes of the next step
+                self.side.wait_event(self.ev_edges)
+                self.exchange_ghosts(Qout)
+                self.qcur = 1 - self.qcur
+                self.planes = self.exchange_qint(Qout, self.qsets[self.qcur])
+                self.ev_comm.record(self.side)
+            main.wait_event(self.ev_comm)
             self.cur = 1 - self.cur
-            self.exchange_ghosts()
 
 
 __all__ = ["SlabLayout", "SlabSolver", "TorchComm", "PATH_A", "PATH_B"]

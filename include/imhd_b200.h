@@ -123,6 +123,12 @@ typedef struct {
 int imhd_step_fused(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
                     const float* qint_wrap, const imhd_slab* s, void* stream);
 
+/* The same step restricted to the output planes [kfrom, kto) of the slab (global indices).  Any split of
+ * the owned range writes the same bits as one imhd_step_fused call: the multi-GPU loop computes the
+ * planes next to the slab ends first, so that their halo exchange overlaps the interior launch. */
+int imhd_step_fused_planes(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
+                           const float* qint_wrap, const imhd_slab* s, int kfrom, int kto, void* stream);
+
 /* e <- p(e,0,0)/(gamma-1) iterated to its fixed point (lib/on-device/kernels_fluidbcs.cu:173,187; every
  * x-thread of the reference launch re-applies it).  Scalar host helper, identity when e == 0. */
 float imhd_wall_energy_fixed_point(float e, int max_iter);

@@ -203,6 +203,24 @@ def test_fused_cell_sets_bit_exact(imhd, torch, O, oracle_mod):
             assert (om.normalised_linf(Q[:, :1], qo[:, :1]) <= 1e-6).all()
 
 
+def test_plane_range_launches_compose(imhd, torch, O, oracle_mod):
+    """imhd_step_fused_planes over any split of the owned planes == one imhd_step_fused call, bit for bit."""
+    om, ops = oracle_mod, imhd.ops
+    dims = (40, 36, 29)
+    Nx, Ny, Nz = dims
+    g, d, Q0 = make_case(O, om, *dims, ic="bennett")
+    for path, D in paths(om):
+        Qin = dev(torch, Q0)
+        ref, out = torch.empty_like(Qin), torch.full_like(Qin, float("nan"))
+        s = ops.make_slab(Nx, Ny, Nz, path, D, DT, *d)
+        q0 = ops.qint_plane(Qin, 0, s)
+        qw = ops.qint_plane(Qin, Nz - 2, s) if path == om.PATH_B else None
+        ops.step_fused(Qin, ref, q0, q0, qw, s)
+        for a, b in ((20, Nz), (0, 5), (5, 6), (6, 20)):   # out of order on purpose
+            ops.step_fused_planes(Qin, out, q0, q0, qw, s, a, b)
+        assert bits_equal(out.cpu().numpy(), ref.cpu().numpy()), path
+
+
 def test_fused_is_chunking_independent(imhd, torch, O, oracle_mod):
     """z-chunks re-derive their predictor planes; any chunk length must give the same bits."""
     om = oracle_mod
@@ -286,11 +304,12 @@ def torch_sync():
 
 
 @pytest.mark.parametrize("world", [2, 3])
-def test_slab_decomposition_is_bit_identical(imhd, torch, O, oracle_mod, world):
+@pytest.mark.parametrize("Nz", [26, 62])  # 62: slabs long enough for the overlapped (ends-first, side-stream) schedule
+def test_slab_decomposition_is_bit_identical(imhd, torch, O, oracle_mod, world, Nz):
     """results must be independent of the number of slabs bit for bit."""
     om = oracle_mod
     slab = __import__("importlib").import_module("imhd-cuda_b200.slab")
-    dims = (36, 30, 26)
+    dims = (36, 30, Nz)
     Nx, Ny, Nz = dims
     g, d, Q0 = make_case(O, om, *dims, ic="bennett")
     for path, D in paths(om):
@@ -304,6 +323,7 @@ def test_slab_decomposition_is_bit_identical(imhd, torch, O, oracle_mod, world):
         def work(r):
             try:
                 s = slab.SlabSolver(Nx, Ny, Nz, path, D, DT, *d, comm=ring.comm(r), corner_e=ce)
+                assert s.overlap == (Nz == 62)
                 s.load_global(Qp)
                 s.step(5)
                 torch.cuda.synchronize()

@@ -50,7 +50,8 @@ class StubCompute:
         out.fill_(1000.0 + k)
         return out
 
-    def step_fused(self, Qin, Qout, lo, hi, wrap, slab):
+    def step_fused_planes(self, Qin, Qout, lo, hi, wrap, slab, kfrom, kto):
+        assert (kfrom, kto) == (slab.k0, slab.k0 + slab.nzl)  # CPU path: no overlap, one launch over the owned planes
         self.seen.append((float(lo[0, 0, 0]), float(hi[0, 0, 0]), None if wrap is None else float(wrap[0, 0, 0])))
         Qout[:, 1:-1] = Qin[:, 1:-1] + 1.0
         if slab.path == 0 and slab.k0 == 0:
