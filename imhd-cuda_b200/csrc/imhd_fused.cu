@@ -111,6 +111,7 @@ __device__ __forceinline__ void qint_cell(const float c[8], const float xp[8], c
 // Corrector at one cell (fast recipe).  q = Q(i,j,k); c, xm, ym, zm = Qint at the cell and at
 // i-1, j-1, k-1; xp, yp, zp = Qint at i+1, j+1, k+1 (path B diffusion only).
 // kernels_od.cu:378-522 / :120-345, LaxWendroffAdv*Local :1206-1332, quirks B-4, B-5, B-6.
+// Must be called by all 32 lanes of a warp whose lanes hold consecutive j (it shuffles).
 // -----------------------------------------------------------------------------------------------
 template <int PATH>
 __device__ __forceinline__ void corr_cell(const float q[8], const float c[8], const float xm[8], const float ym[8],
@@ -122,7 +123,10 @@ __device__ __forceinline__ void corr_cell(const float q[8], const float c[8], co
     flux_loc<DIR_Y>(c, sc, gc);
     flux_loc<DIR_Z>(c, sc, hc);
     flux_loc<DIR_X>(xm, make_prim(xm), fi);
-    flux_loc<DIR_Y>(ym, make_prim(ym), gj);
+    // G'(Qint(i,j-1,k)) is what lane-1 has just computed as its own gc (same inputs, same function, same bits): one
+    // shuffle per component instead of re-deriving the neighbour's primitives and flux.  Lane 0 never writes output.
+#pragma unroll
+    for (int v = 0; v < 8; ++v) gj[v] = v == BY ? 0.0f : __shfl_up_sync(0xffffffffu, gc[v], 1);
     {   // k-1 point with the reference's mixed neighbours: Bsq from (Bx(i-1), By(j-1), Bz(k-1)) (B-4), Bdotu with
         // rhovy(j-1) (B-5); KE and the velocities from the k-1 state itself
         Prim sk;
