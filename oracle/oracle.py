@@ -4,6 +4,8 @@
 * ``Reference`` -- oracle/_ref/libimhd_ref_cpu.so, the reference's own unmodified kernel
   sources compiled for the host (oracle/Makefile ``ref``; needs /root/reference to BUILD,
   the prebuilt .so travels to the GPU box).
+* ``ReferenceGPU`` -- oracle/_ref/libimhd_ref_gpu[_nofma].so, the same sources compiled by nvcc
+  for sm_100 (oracle/Makefile ``refgpu``): the kernels to beat, and a parity pin on the B200.
 
 Only tests/, ``__graft_entry__.smoke()`` and bench.py's ``cpu_baseline`` / ``--impl
 reference`` legs may import this module; the product package never does.
@@ -34,6 +36,7 @@ def build(ref: bool | None = None) -> None:
         ref = os.path.isdir("/root/reference/lib/on-device")
     if ref:
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+        subprocess.check_call(["make", "-s", "-j4", "-C", HERE, "refgpu"])
 
 
 def _ptr(a: np.ndarray):
@@ -225,6 +228,60 @@ class Reference(_Lib):
             self.lib.ref_pathA_steps(_ptr(Q), _ptr(Qint), nsteps, dt, dx, dy, dz, *d, self.T)
         else:
             self.lib.ref_pathB_steps(_ptr(Q), _ptr(Qint), nsteps, D, dt, dx, dy, dz, *d, self.T)
+
+
+class ReferenceGPU(_Lib):
+    """The reference's own kernels compiled by nvcc for sm_100 (oracle/_ref/libimhd_ref_gpu*.so), driven in the
+    order of its two drivers on DEVICE pointers (ints).  ``nofma=True`` loads the -fmad=false build, whose rounding
+    points equal the source's (bit-comparable with the host build); the default is the reference's stock flags.
+
+    geometry = (bx, by, bz, cover, mx, my, mz, bc_z1): see oracle/ref_shim/ref_gpu_harness.cu."""
+
+    kind = "reference-gpu"
+    STOCK_A = (6, 6, 6, 0, 3, 3, 3, 0)      # build/on-device/input.inp:27-29,45-47
+    COVER_A = (8, 8, 4, 1, 3, 3, 3, 0)      # 256 threads: the correctors need 160 / 255 registers per thread
+    COVER_B = (8, 8, 4, 1, 1, 1, 1, 1)      # deterministic BoundaryConditions (z-extent 1)
+    COALESCED_A = (1, 32, 8, 1, 3, 3, 3, 0)  # warp lanes along j (unit stride): the friendliest block shape
+    COALESCED_B = (1, 32, 8, 1, 1, 1, 1, 1)
+
+    def __init__(self, nofma: bool = False):
+        super().__init__(os.path.join(HERE, "_ref", "libimhd_ref_gpu_nofma.so" if nofma else "libimhd_ref_gpu.so"))
+        dims = [_i, _i, _i]
+        for name, args in (("refgpu_pathA_prime", [_p, _p, _f, _f, _f, _f] + dims + [_p]),
+                           ("refgpu_pathA_steps", [_p, _p, _i, _f, _f, _f, _f] + dims + [_p, _p]),
+                           ("refgpu_pathB_prime", [_p, _p, _f, _f, _f, _f, _f] + dims + [_p]),
+                           ("refgpu_pathB_steps", [_p, _p, _i, _f, _f, _f, _f, _f] + dims + [_p, _p]),
+                           ("refgpu_covers", [_p] + dims), ("refgpu_num_sms", [])):
+            fn = getattr(self.lib, name)
+            fn.argtypes, fn.restype = args, _i
+
+    @staticmethod
+    def _geom(g):
+        return (C.c_int * 8)(*[int(v) for v in g])
+
+    def covers(self, g, Nx, Ny, Nz):
+        return bool(self.lib.refgpu_covers(self._geom(g), Nx, Ny, Nz))
+
+    def prime(self, Qptr, Qintptr, dims, path, D, dt, dx, dy, dz, geom):
+        Nx, Ny, Nz = dims
+        if path == PATH_A:
+            rc = self.lib.refgpu_pathA_prime(Qptr, Qintptr, dt, dx, dy, dz, Nx, Ny, Nz, self._geom(geom))
+        else:
+            rc = self.lib.refgpu_pathB_prime(Qptr, Qintptr, D, dt, dx, dy, dz, Nx, Ny, Nz, self._geom(geom))
+        if rc:
+            raise RuntimeError(f"reference GPU kernels failed: cudaError {rc}")
+
+    def steps(self, Qptr, Qintptr, dims, path, nsteps, D, dt, dx, dy, dz, geom):
+        """Returns ms = [corrector, fluid BCs, predictor, Qint boundary, total] summed over nsteps."""
+        Nx, Ny, Nz = dims
+        ms = (C.c_float * 5)()
+        if path == PATH_A:
+            rc = self.lib.refgpu_pathA_steps(Qptr, Qintptr, nsteps, dt, dx, dy, dz, Nx, Ny, Nz, self._geom(geom), ms)
+        else:
+            rc = self.lib.refgpu_pathB_steps(Qptr, Qintptr, nsteps, D, dt, dx, dy, dz, Nx, Ny, Nz, self._geom(geom), ms)
+        if rc:
+            raise RuntimeError(f"reference GPU kernels failed: cudaError {rc}")
+        return list(ms)
 
 
 def best_available():

@@ -1,0 +1,102 @@
+"""GPU parity against the reference ITSELF run on the B200: its unmodified kernels compiled by nvcc for sm_100
+(oracle/_ref/libimhd_ref_gpu*.so, built by `make -C oracle refgpu` where /root/reference exists; the .so travels
+to the GPU box).  Complements test_gpu_parity.py, whose checker is the reference compiled for the host.
+
+  * -fmad=false build: rounding points == source.  The host build of the same sources must agree (pins the host
+    oracle to the device semantics: CUDA libdevice pow / f64 division vs glibc), and so must our granular kernels.
+  * stock build (default -fmad): the fused hot path must stay inside the 1e-5 bar against it after 100 steps at C1.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import bits_equal, make_case
+from test_oracle_golden import random_state
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFDIR = os.path.join(os.path.dirname(HERE), "oracle", "_ref")
+DT, D_B, TOL = 1e-4, 0.01, 1e-5
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+
+    if not t.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    return t
+
+
+def refgpu(oracle_mod, nofma):
+    try:
+        return oracle_mod.ReferenceGPU(nofma=nofma)
+    except (FileNotFoundError, OSError):
+        pytest.skip("oracle/_ref/libimhd_ref_gpu*.so not built (needs /root/reference at build time)")
+
+
+def run_ref_gpu(torch, G, Q0, path, D, d, nsteps, geom):
+    _, Nz, Nx, Ny = Q0.shape
+    Q = torch.from_numpy(Q0.copy()).cuda()
+    Qint = torch.zeros_like(Q)
+    assert G.covers(geom, Nx, Ny, Nz)
+    G.prime(Q.data_ptr(), Qint.data_ptr(), (Nx, Ny, Nz), path, D, DT, *d, geom)
+    if nsteps:
+        G.steps(Q.data_ptr(), Qint.data_ptr(), (Nx, Ny, Nz), path, nsteps, D, DT, *d, geom)
+    torch.cuda.synchronize()
+    return Q.cpu().numpy(), Qint.cpu().numpy()
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+@pytest.mark.parametrize("ic", ["screwpinch", "random"])
+def test_reference_on_gpu_agrees_with_its_host_build_and_with_granular(imhd, torch, O, R, oracle_mod, tag, ic):
+    G = refgpu(oracle_mod, nofma=True)
+    path, D = (oracle_mod.PATH_A, 0.0) if tag == "A" else (oracle_mod.PATH_B, D_B)
+    dims = (46, 38, 19)
+    _, d, Q0 = make_case(O, oracle_mod, *dims)
+    if ic == "random":
+        Q0 = random_state(*dims, seed=11)
+    geom = G.COVER_A if tag == "A" else G.COVER_B
+    nsteps = 3
+    Qg, Qig = run_ref_gpu(torch, G, Q0, path, D, d, nsteps, geom)
+
+    # the host build of the same sources
+    Qh, Qih = Q0.copy(), np.zeros_like(Q0)
+    R.prime(Qh, Qih, path, D, DT, *d)
+    R.steps(Qh, Qih, path, nsteps, D, DT, *d)
+    eq = np.isclose(Qg, Qh, rtol=0, atol=0, equal_nan=True)
+    err = oracle_mod.normalised_linf(np.nan_to_num(Qg), np.nan_to_num(Qh)).max()
+    print(f"\nreference sm_100 (-fmad=false) vs reference host, path {tag} {ic}: bit-equal cells {eq.mean():.6f}, nLinf {err:.2e}")
+    assert err <= 1e-6
+
+    # our parity-granular operators through the C ABI
+    with imhd.ops.Context(*dims) as ctx:
+        ctx.set_state(Q0)
+        ctx.set_spacing(*d)
+        ctx.prime(path, D, DT)
+        ctx.step_granular(nsteps)
+        Qo = ctx.get_state()
+    err2 = oracle_mod.normalised_linf(np.nan_to_num(Qo), np.nan_to_num(Qg)).max()
+    print(f"granular (C ABI) vs reference sm_100 (-fmad=false): bit-equal {bits_equal(Qo, Qg)}, nLinf {err2:.2e}")
+    assert err2 <= 1e-6
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_fused_c1_100_steps_vs_reference_kernels_on_the_same_gpu(imhd, torch, O, oracle_mod, tag):
+    G = refgpu(oracle_mod, nofma=False)  # stock flags
+    path, D = (oracle_mod.PATH_A, 0.0) if tag == "A" else (oracle_mod.PATH_B, D_B)
+    dims = (64, 64, 128)  # C1
+    _, d, Q0 = make_case(O, oracle_mod, *dims)
+    geom = G.COVER_A if tag == "A" else G.COVER_B
+    Qr, _ = run_ref_gpu(torch, G, Q0, path, D, d, 100, geom)
+    with imhd.ops.Context(*dims) as ctx:
+        ctx.set_state(Q0)
+        ctx.set_spacing(*d)
+        ctx.prime(path, D, DT)
+        ctx.step(100)
+        Qf = ctx.get_state()
+    assert np.isfinite(Qr).all() and np.isfinite(Qf).all()
+    err = oracle_mod.normalised_linf(Qf, Qr)
+    print(f"\nfused vs reference kernels on sm_100 (stock flags), C1 path {tag}, 100 steps: nLinf per variable {err}")
+    assert err.max() <= TOL
