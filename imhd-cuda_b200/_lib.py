@@ -43,6 +43,9 @@ SIGNATURES = {
     "imhd_init_grids": (_i, [_p, _p, _p] + [_f] * 6 + _dims + [_p]),
     "imhd_init_screwpinch_stride": (_i, [_p, _f, _p, _p, _p] + _dims + [_p]),
     "imhd_init_cubic_bennett_vortex_m0": (_i, [_p, _f, _f, _p, _p, _p] + _dims + [_p]),
+    "imhd_init_cubic_bennett_vortex": (_i, [_p, _p, _p, _p] + _dims + [_p]),
+    "imhd_init_zpinch": (_i, [_p, _f, _p, _p, _p] + _dims + [_p]),
+    "imhd_init_screwpinch": (_i, [_p, _f, _f, _p, _p, _p] + _dims + [_p]),
     "imhd_step_fused": (_i, [_p, _p, _p, _p, _p, C.POINTER(Slab), _p]),
     "imhd_step_fused_planes": (_i, [_p, _p, _p, _p, _p, C.POINTER(Slab), _i, _i, _p]),
     "imhd_wall_energy_fixed_point": (_f, [_f, _i]),
@@ -54,6 +57,11 @@ SIGNATURES = {
     "imhd_ctx_init_grids": (_i, [_p] + [_f] * 6),
     "imhd_ctx_init_screwpinch_stride": (_i, [_p, _f]),
     "imhd_ctx_init_cubic_bennett_vortex_m0": (_i, [_p, _f, _f]),
+    "imhd_registry_count": (_i, [_i]),
+    "imhd_registry_name": (C.c_char_p, [_i, _i]),
+    "imhd_registry_initializer_nparams": (_i, [C.c_char_p]),
+    "imhd_ctx_initialize": (_i, [_p, C.c_char_p, _p, _i]),
+    "imhd_registry_resolve_path": (_i, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(_i)]),
     "imhd_ctx_set_state": (_i, [_p, _p]),
     "imhd_ctx_set_spacing": (_i, [_p, _f, _f, _f]),
     "imhd_ctx_prime": (_i, [_p, _i, _f, _f]),

@@ -162,6 +162,135 @@ extern "C" int imhd_ctx_init_cubic_bennett_vortex_m0(imhd_ctx* c, float k, float
     return imhd_init_cubic_bennett_vortex_m0(c->buf[c->cur], k, A, c->gx, c->gy, c->gz, c->Nx, c->Ny, c->Nz, c->stream);
 }
 
+// ---- string-keyed registry: the reference's planned plugin surface (include/on-device/utils/configurers.hpp) ----------
+// SimulationInitializer (:13-41), FluidKernelConfigurer (:47-72), PredictorKernelConfigurer (:78-110),
+// FluidBoundaryConfigurer (:127-148), PredictorBoundaryConfigurer (:180-196).  The reference's keys are kept; keys it
+// does not have yet (its "ADD OTHER INITIALIZERS" / "ADD MORE BUNDLES" slots) are marked ext.
+namespace {
+
+struct IcEntry {
+    const char* name;
+    int nparams;
+    int (*launch)(imhd_ctx*, const float*);
+};
+
+int ic_screwpinch(imhd_ctx* c, const float* p) {
+    // ScrewPinch leaves seven variables untouched outside the pinch (initialize_od.cu:237): give them a defined value
+    IMHD_CUDA(cudaMemsetAsync(c->buf[c->cur], 0, 8 * c->cells * sizeof(float), c->stream));
+    return imhd_init_screwpinch(c->buf[c->cur], p[0], p[1], c->gx, c->gy, c->gz, c->Nx, c->Ny, c->Nz, c->stream);
+}
+int ic_screwpinch_stride(imhd_ctx* c, const float* p) {
+    return imhd_init_screwpinch_stride(c->buf[c->cur], p[0], c->gx, c->gy, c->gz, c->Nx, c->Ny, c->Nz, c->stream);
+}
+int ic_bennett(imhd_ctx* c, const float*) {
+    return imhd_init_cubic_bennett_vortex(c->buf[c->cur], c->gx, c->gy, c->gz, c->Nx, c->Ny, c->Nz, c->stream);
+}
+int ic_bennett_m0(imhd_ctx* c, const float* p) {
+    return imhd_init_cubic_bennett_vortex_m0(c->buf[c->cur], p[0], p[1], c->gx, c->gy, c->gz, c->Nx, c->Ny, c->Nz, c->stream);
+}
+int ic_zpinch(imhd_ctx* c, const float* p) {
+    return imhd_init_zpinch(c->buf[c->cur], p[0], c->gx, c->gy, c->gz, c->Nx, c->Ny, c->Nz, c->stream);
+}
+
+const IcEntry kInitializers[] = {
+    {"screwpinch", 2, ic_screwpinch},                  // J0, r_max_coeff            configurers.hpp:21
+    {"screwpinch-stride", 1, ic_screwpinch_stride},    // J0                         :24
+    {"cubic-bennett-vortex", 0, ic_bennett},           //                            :27
+    {"cubic-bennett-vortex-m0", 2, ic_bennett_m0},     // k, A                       ext (no_diffusion.cu:168)
+    {"zpinch", 1, ic_zpinch},                          // r_max_coeff                ext (no_diffusion.cu:169)
+};
+
+struct BundleEntry {
+    const char* name;
+    int path;  // IMHD_PATH_A, IMHD_PATH_B, or -1 = either
+};
+const BundleEntry kCorrectors[] = {{"fluidadvancelocal-nodiff", IMHD_PATH_A},   // configurers.hpp:54
+                                   {"fluidadvancelocal", IMHD_PATH_B}};         // ext (main.cu:202)
+const BundleEntry kPredictors[] = {{"corrector_advance-tp_nodiff", IMHD_PATH_A},      // :87
+                                   {"corrector_advance-stride_nodiff", IMHD_PATH_A},  // :90 (same arithmetic, other launch shape)
+                                   {"corrector_advance-stride", IMHD_PATH_B}};        // ext (main.cu:207)
+const BundleEntry kFluidBcs[] = {{"pcrw-xy_pbc-z", -1}};                        // :130
+const BundleEntry kPredictorBcs[] = {{"pbc-z", -1}};                            // :185
+
+template <class T, int N>
+constexpr int count_of(const T (&)[N]) { return N; }
+
+const BundleEntry* find_bundle(const BundleEntry* t, int n, const char* key) {
+    for (int q = 0; q < n; ++q)
+        if (key && !strcmp(t[q].name, key)) return &t[q];
+    return nullptr;
+}
+
+}  // namespace
+
+extern "C" int imhd_registry_count(int kind) {
+    switch (kind) {
+        case IMHD_REG_INITIALIZER: return count_of(kInitializers);
+        case IMHD_REG_CORRECTOR: return count_of(kCorrectors);
+        case IMHD_REG_PREDICTOR: return count_of(kPredictors);
+        case IMHD_REG_FLUID_BCS: return count_of(kFluidBcs);
+        case IMHD_REG_PREDICTOR_BCS: return count_of(kPredictorBcs);
+    }
+    return 0;
+}
+
+extern "C" const char* imhd_registry_name(int kind, int index) {
+    if (index < 0 || index >= imhd_registry_count(kind)) return nullptr;
+    switch (kind) {
+        case IMHD_REG_INITIALIZER: return kInitializers[index].name;
+        case IMHD_REG_CORRECTOR: return kCorrectors[index].name;
+        case IMHD_REG_PREDICTOR: return kPredictors[index].name;
+        case IMHD_REG_FLUID_BCS: return kFluidBcs[index].name;
+        case IMHD_REG_PREDICTOR_BCS: return kPredictorBcs[index].name;
+    }
+    return nullptr;
+}
+
+extern "C" int imhd_registry_initializer_nparams(const char* sim_type) {
+    for (const IcEntry& e : kInitializers)
+        if (sim_type && !strcmp(e.name, sim_type)) return e.nparams;
+    return -1;
+}
+
+extern "C" int imhd_ctx_initialize(imhd_ctx* c, const char* sim_type, const float* params, int nparams) {
+    CTX_CHECK(c);
+    if (int e = need_grids(c)) return e;
+    for (const IcEntry& e : kInitializers) {
+        if (!sim_type || strcmp(e.name, sim_type)) continue;
+        if (nparams != e.nparams || (e.nparams && !params)) {
+            set_error("imhd_ctx_initialize: \"%s\" takes %d parameter(s), got %d", e.name, e.nparams, nparams);
+            return IMHD_E_INVALID;
+        }
+        c->primed = false;
+        return e.launch(c, params);
+    }
+    set_error("Unknown simulation type: %s", sim_type ? sim_type : "(null)");  // configurers.hpp:36
+    return IMHD_E_INVALID;
+}
+
+extern "C" int imhd_registry_resolve_path(const char* corrector, const char* predictor, const char* fluid_bcs,
+                                          const char* predictor_bcs, int* path) {
+    const BundleEntry* co = find_bundle(kCorrectors, count_of(kCorrectors), corrector);
+    if (!co) { set_error("Unknown kernel bundle selected: %s", corrector ? corrector : "(null)"); return IMHD_E_INVALID; }   // :67
+    const BundleEntry* pr = find_bundle(kPredictors, count_of(kPredictors), predictor);
+    if (!pr) { set_error("Unknown I.V. kernel bundle selection: %s", predictor ? predictor : "(null)"); return IMHD_E_INVALID; }  // :105
+    if (!find_bundle(kFluidBcs, count_of(kFluidBcs), fluid_bcs)) {
+        set_error("Unknown bcs selected: %s", fluid_bcs ? fluid_bcs : "(null)");  // :144
+        return IMHD_E_INVALID;
+    }
+    if (!find_bundle(kPredictorBcs, count_of(kPredictorBcs), predictor_bcs)) {
+        set_error("Unknown bcs selected: %s", predictor_bcs ? predictor_bcs : "(null)");  // :192
+        return IMHD_E_INVALID;
+    }
+    if (co->path != pr->path) {
+        set_error("corrector bundle \"%s\" and predictor bundle \"%s\" belong to different time loops (with / without diffusion)",
+                  co->name, pr->name);
+        return IMHD_E_INVALID;
+    }
+    if (path) *path = co->path;
+    return 0;
+}
+
 extern "C" int imhd_ctx_set_state(imhd_ctx* c, const float* host_Q) {
     CTX_CHECK(c);
     if (!host_Q) { set_error("imhd_ctx_set_state: null host buffer"); return IMHD_E_INVALID; }

@@ -7,7 +7,10 @@
 // The execution-configuration arguments (block dims, SM multipliers) are accepted and ignored: the library picks its
 // own tiling.  The writer/attribute/grid binary names and num_proc are accepted and unused (output is in-process);
 // eigen_bin_name other than "none" prints a notice (the Eigen CFL scanner is out of scope).
-// Optional environment: IMHD_OUTPUT_EVERY=n (default 1 = the reference's behaviour), IMHD_DEVICE=d.
+// Optional environment: IMHD_OUTPUT_EVERY=n (default 1 = the reference's behaviour), IMHD_DEVICE=d,
+// IMHD_IC=<registry key>[:p0[,p1]] selects the initial condition by the reference's registry key
+// (include/on-device/utils/configurers.hpp:21-29) instead of the one each shipped driver hard-codes; parameters left
+// out come from argv (J0, r_max_coeff, A, k_harmonic) where the argv list has them.
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -37,7 +40,9 @@ int main(int argc, char* argv[]) {
     const int Nt = atoi(argv[a++]), Nx = atoi(argv[a++]), Ny = atoi(argv[a++]), Nz = atoi(argv[a++]);
     const float J0 = atof(argv[a++]), D = atof(argv[a++]);
 #ifdef IMHD_NODIFF
-    a++;  // r_max_coeff: parsed and unused by the shipped initial condition (no_diffusion.cu:27, B-24)
+    const float r_max_coeff = atof(argv[a++]);  // parsed and unused by the shipped initial condition (no_diffusion.cu:27, B-24)
+#else
+    const float r_max_coeff = 0.25f;
 #endif
     const float x_min = atof(argv[a++]), x_max = atof(argv[a++]), y_min = atof(argv[a++]), y_max = atof(argv[a++]);
     const float z_min = atof(argv[a++]), z_max = atof(argv[a++]), dt = atof(argv[a++]);
@@ -59,11 +64,30 @@ int main(int argc, char* argv[]) {
     CHECK(imhd_ctx_init_grids(ctx, x_min, x_max, y_min, y_max, z_min, z_max));
 #ifdef IMHD_NODIFF
     const float k = 2 * M_PI * n_harmonic / (z_max - z_min);  // no_diffusion.cu:166
-    CHECK(imhd_ctx_init_cubic_bennett_vortex_m0(ctx, k, A));
-    (void)J0;
+    std::string ic = "cubic-bennett-vortex-m0";                // no_diffusion.cu:168
 #else
-    CHECK(imhd_ctx_init_screwpinch_stride(ctx, J0));
+    const float k = 0.f, A = 0.f;
+    std::string ic = "screwpinch-stride";                      // main.cu:105
 #endif
+    float ic_params[2] = {0.f, 0.f};
+    int ic_given = 0;
+    if (const char* sel = getenv("IMHD_IC")) {
+        ic = sel;
+        const size_t colon = ic.find(':');
+        if (colon != std::string::npos) {
+            ic_given = sscanf(ic.c_str() + colon + 1, "%f,%f", &ic_params[0], &ic_params[1]);
+            ic.resize(colon);
+        }
+    }
+    const int ic_n = imhd_registry_initializer_nparams(ic.c_str());
+    if (ic_given < ic_n) {  // defaults from argv
+        const float d0 = ic == "zpinch" ? r_max_coeff : ic == "cubic-bennett-vortex-m0" ? k : J0;
+        const float d1 = ic == "cubic-bennett-vortex-m0" ? A : r_max_coeff;
+        if (ic_given < 1) ic_params[0] = d0;
+        if (ic_given < 2) ic_params[1] = d1;
+    }
+    printf("Initial condition: %s\n", ic.c_str());
+    CHECK(imhd_ctx_initialize(ctx, ic.c_str(), ic_params, ic_n < 0 ? 0 : ic_n));
     CHECK(imhd_ctx_prime(ctx, path, D, dt));
 
     printf("Writing initial conditions and grid to %s\n", path_to_data.c_str());

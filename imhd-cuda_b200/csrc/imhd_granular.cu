@@ -250,26 +250,35 @@ __device__ __forceinline__ float total_energy(const float U[8], float p) {  // :
                    0.5 * (sqd(U[BX]) + sqd(U[BY]) + sqd(U[BZ])));
 }
 
-template <int IC>  // 0 = ScrewPinchStride, 1 = CubicBennettVortex_m0
-__global__ void __launch_bounds__(256) k_init_state(float* __restrict__ Q, float J0_or_k, float A, const float* __restrict__ gx,
+// IC: 0 ScrewPinchStride(a=J0)  1 CubicBennettVortex_m0(a=k,b=A)  2 CubicBennettVortex  3 ZPinch(a=r_max_coeff)
+//     4 ScrewPinch(a=J0,b=r_max_coeff)   (initialize_od.cu:269, 132, 59, 347, 207)
+template <int IC>
+__global__ void __launch_bounds__(256) k_init_state(float* __restrict__ Q, float a, float b, const float* __restrict__ gx,
                                                     const float* __restrict__ gy, const float* __restrict__ gz, Params P) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y * blockDim.y + threadIdx.y;
     const int k = blockIdx.z;
     if (i >= P.Nx || j >= P.Ny) return;
     const long long vs = P.cube, l = (long long)k * P.plane + (long long)i * P.Ny + j;
-    const float r_pinch = (float)(0.25 * sqrtf((float)(sqd(gx[P.Nx - 1]) + sqd(gy[P.Ny - 1]))));
+    const float r_max = sqrtf((float)(sqd(gx[P.Nx - 1]) + sqd(gy[P.Ny - 1])));
+    // 0.25 is a double literal in the stride / Bennett kernels; r_max_coeff is an fp32 argument (:219, :359)
+    const float r_pinch = (IC == 3) ? a * r_max : (IC == 4) ? b * r_max : (float)(0.25 * r_max);
     const float x = gx[i], y = gy[j];
     const float r = sqrtf((float)(sqd(x) + sqd(y)));
+    if (IC == 4 && !(r < r_pinch)) {  // ScrewPinch writes only rho outside the pinch (:237); the rest is left as found
+        Q[l] = 0.1f;
+        return;
+    }
     float U[8] = {0.01f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (r < r_pinch) {
         const double r2 = sqd(r), rp2 = sqd(r_pinch);
-        if (IC == 0) {
-            const float J0 = J0_or_k;
-            const float Jr = 0.0f, Jphi = 0.0f, Br = 0.0f;
-            const float Btheta = (float)(0.5 * J0 * r * (1.0 - 0.5 * r2 / rp2));  // :313
+        const float Br = 0.0f;
+        if (IC == 0 || IC == 4) {
+            const float J0 = a;
+            const float Jr = 0.0f, Jphi = 0.0f;
+            const float Btheta = (float)(0.5 * J0 * r * (1.0 - 0.5 * r2 / rp2));  // :313 / :243
             const double rp4 = rp2 * rp2, r4 = r2 * r2, r6 = r4 * r2;             // pow(.,4), pow(.,6)
-            const float p = (float)(-0.25 * (sqd(J0) / rp4) * (r6 / 6.0 - 0.75 * rp2 * r4 + rp4 * r2));  // :316
+            const float p = (float)(-0.25 * (sqd(J0) / rp4) * (r6 / 6.0 - 0.75 * rp2 * r4 + rp4 * r2));  // :316 / :246
             U[RHO] = 1.0f;
             U[MX] = Jr * x - Jphi * y / r;
             U[MY] = Jr * y + Jphi * x / r;
@@ -278,16 +287,35 @@ __global__ void __launch_bounds__(256) k_init_state(float* __restrict__ Q, float
             U[BY] = Br * y + Btheta * x / r;
             U[BZ] = 1.0f;
             U[EN] = total_energy(U, p);
-        } else {
-            const float phi = r, Br = 0.0f, z = gz[k];
+        } else if (IC == 1 || IC == 2) {
+            const float phi = r;
             const double phi3 = r2 * (double)phi;
             const float Btheta = (float)(-(1) * (phi3 - 3 * r2 - 6 * phi + 6 * (phi + 1) * logf(phi + 1)) /
-                                         (2 * phi * (phi + 1)));                       // :177
-            const float p = (float)(1 - phi3 / sqd(phi + 1) * (phi - 10));          // :180
-            U[RHO] = (float)(1.0 + A * cosf(k * z));  // the z loop index shadows the wavenumber (:158,183)
-            U[MZ] = (float)((1) * r2 / sqd(phi + 1));
-            U[BX] = Br * x - Btheta * y / phi;
-            U[BY] = Br * y + Btheta * x / phi;
+                                         (2 * phi * (phi + 1)));                       // :177 / :101
+            if (IC == 1) {
+                const float z = gz[k];
+                const float p = (float)(1 - phi3 / sqd(phi + 1) * (phi - 10));      // :180
+                U[RHO] = (float)(1.0 + b * cosf(k * z));  // the z loop index shadows the wavenumber (:158,183)
+                U[MZ] = (float)((1) * r2 / sqd(phi + 1));
+                U[BX] = Br * x - Btheta * y / phi;
+                U[BY] = Br * y + Btheta * x / phi;
+                U[EN] = total_energy(U, p);
+            } else {
+                const float p = (float)phi3;                                         // :103
+                U[RHO] = 1.0f;
+                U[MZ] = (float)(r2 / sqd(phi + 1));
+                U[BX] = Br * x - Btheta * y / phi;
+                U[BY] = Br * y + Btheta * x / phi;
+                U[EN] = total_energy(U, p);
+            }
+        } else {  // ZPinch
+            const double r3 = r2 * (double)r, r4 = r2 * r2, r6 = r4 * r2, rp4 = rp2 * rp2, rp6 = rp4 * rp2;
+            const float Btheta = (float)(0.5 * (r + 0.5 * r3 / rp2));                                           // :394
+            const float p = (float)(1 + 0.5 * (0.5 * r2 / rp2 + 0.375 * r4 / rp4 - (1.0 / 12.0) * r6 / rp6));  // :398
+            U[RHO] = 1.0f;
+            U[MZ] = (float)(1 + r2 / rp2);
+            U[BX] = Br * x - Btheta * y / r;
+            U[BY] = Br * y + Btheta * x / r;
             U[EN] = total_energy(U, p);
         }
     }
@@ -379,6 +407,33 @@ extern "C" int imhd_init_cubic_bennett_vortex_m0(float* Q, float k, float A, con
     if (int e = bad_dims(Nx, Ny, Nz)) return e;
     const Params P = make_params(0, 0.f, 1.f, 1.f, 1.f, 1.f, Nx, Ny, Nz);
     k_init_state<1><<<cell_grid(P, Nz), kCellBlock, 0, (cudaStream_t)stream>>>(Q, k, A, x, y, z, P);
+    IMHD_LAUNCH_CHECK(1);
+    return 0;
+}
+
+extern "C" int imhd_init_cubic_bennett_vortex(float* Q, const float* x, const float* y, const float* z, int Nx, int Ny,
+                                              int Nz, void* stream) {
+    if (int e = bad_dims(Nx, Ny, Nz)) return e;
+    const Params P = make_params(0, 0.f, 1.f, 1.f, 1.f, 1.f, Nx, Ny, Nz);
+    k_init_state<2><<<cell_grid(P, Nz), kCellBlock, 0, (cudaStream_t)stream>>>(Q, 0.f, 0.f, x, y, z, P);
+    IMHD_LAUNCH_CHECK(1);
+    return 0;
+}
+
+extern "C" int imhd_init_zpinch(float* Q, float r_max_coeff, const float* x, const float* y, const float* z, int Nx,
+                                int Ny, int Nz, void* stream) {
+    if (int e = bad_dims(Nx, Ny, Nz)) return e;
+    const Params P = make_params(0, 0.f, 1.f, 1.f, 1.f, 1.f, Nx, Ny, Nz);
+    k_init_state<3><<<cell_grid(P, Nz), kCellBlock, 0, (cudaStream_t)stream>>>(Q, r_max_coeff, 0.f, x, y, z, P);
+    IMHD_LAUNCH_CHECK(1);
+    return 0;
+}
+
+extern "C" int imhd_init_screwpinch(float* Q, float J0, float r_max_coeff, const float* x, const float* y,
+                                    const float* z, int Nx, int Ny, int Nz, void* stream) {
+    if (int e = bad_dims(Nx, Ny, Nz)) return e;
+    const Params P = make_params(0, 0.f, 1.f, 1.f, 1.f, 1.f, Nx, Ny, Nz);
+    k_init_state<4><<<cell_grid(P, Nz), kCellBlock, 0, (cudaStream_t)stream>>>(Q, J0, r_max_coeff, x, y, z, P);
     IMHD_LAUNCH_CHECK(1);
     return 0;
 }

@@ -99,6 +99,54 @@ def init_cubic_bennett_vortex_m0(k, A, x, y, z):
     return Q
 
 
+def _init_ic(fn_name, x, y, z, *scalars, prefill=None):
+    import torch
+
+    L = _lib.load()
+    shape = (8, len(z), len(x), len(y))
+    Q = torch.empty(shape, dtype=torch.float32, device=x.device) if prefill is None else prefill.clone()
+    check(getattr(L, fn_name)(_dev(Q), *scalars, _dev(x), _dev(y), _dev(z), len(x), len(y), len(z), _stream()))
+    return Q
+
+
+def init_cubic_bennett_vortex(x, y, z):
+    """CubicBennettVortex (lib/on-device/initialize_od.cu:59-130)."""
+    return _init_ic("imhd_init_cubic_bennett_vortex", x, y, z)
+
+
+def init_zpinch(r_max_coeff, x, y, z):
+    """ZPinch (lib/on-device/initialize_od.cu:347-424)."""
+    return _init_ic("imhd_init_zpinch", x, y, z, r_max_coeff)
+
+
+def init_screwpinch(J0, r_max_coeff, x, y, z, prefill=None):
+    """ScrewPinch (lib/on-device/initialize_od.cu:207-267).  Outside the pinch only rho is written; the other seven
+    variables keep the contents of ``prefill`` (the reference leaves its cudaMalloc as it found it)."""
+    import torch
+
+    if prefill is None:
+        prefill = torch.zeros((8, len(z), len(x), len(y)), dtype=torch.float32, device=x.device)
+    return _init_ic("imhd_init_screwpinch", x, y, z, J0, r_max_coeff, prefill=prefill)
+
+
+# ---- registry (include/on-device/utils/configurers.hpp) ------------------------------------------------
+REG_INITIALIZER, REG_CORRECTOR, REG_PREDICTOR, REG_FLUID_BCS, REG_PREDICTOR_BCS = range(5)
+
+
+def registry_names(kind: int) -> list[str]:
+    L = _lib.load()
+    return [L.imhd_registry_name(kind, q).decode() for q in range(L.imhd_registry_count(kind))]
+
+
+def registry_resolve_path(corrector: str, predictor: str, fluid_bcs: str = "pcrw-xy_pbc-z",
+                          predictor_bcs: str = "pbc-z") -> int:
+    L = _lib.load()
+    path = C.c_int(-1)
+    check(L.imhd_registry_resolve_path(corrector.encode(), predictor.encode(), fluid_bcs.encode(),
+                                       predictor_bcs.encode(), C.byref(path)))
+    return path.value
+
+
 # ---- fused step -----------------------------------------------------------------------------------
 def make_slab(Nx, Ny, Nz, path, D, dt, dx, dy, dz, k0=0, nzl=None, ghosts=0, corner_e=0.0) -> Slab:
     return Slab(Nx, Ny, Nz, k0, Nz if nzl is None else nzl, ghosts, path, D, dt, dx, dy, dz, corner_e)
@@ -183,6 +231,11 @@ class Context:
 
     def init_cubic_bennett_vortex_m0(self, k, A):
         check(self.L.imhd_ctx_init_cubic_bennett_vortex_m0(self.h, k, A))
+
+    def initialize(self, sim_type: str, *params: float):
+        """SimulationInitializer::initialize (configurers.hpp:32-39): IC kernel by registry key."""
+        arr = (C.c_float * max(1, len(params)))(*params)
+        check(self.L.imhd_ctx_initialize(self.h, sim_type.encode(), arr, len(params)))
 
     def set_state(self, Q: np.ndarray):
         Q = np.ascontiguousarray(Q, dtype=np.float32)

@@ -92,6 +92,15 @@ int imhd_init_screwpinch_stride(float* Q, float J0, const float* x, const float*
  * z loop index. */
 int imhd_init_cubic_bennett_vortex_m0(float* Q, float k, float A, const float* x, const float* y,
                                       const float* z, int Nx, int Ny, int Nz, void* stream);
+/* The three initial conditions the shipped drivers keep commented out (no_diffusion.cu:169-171):
+ * CubicBennettVortex (:59-130), ZPinch (:347-424), ScrewPinch (:207-267; outside the pinch it writes only
+ * rho = 0.1 and leaves the other seven variables as it found them). */
+int imhd_init_cubic_bennett_vortex(float* Q, const float* x, const float* y, const float* z, int Nx, int Ny,
+                                   int Nz, void* stream);
+int imhd_init_zpinch(float* Q, float r_max_coeff, const float* x, const float* y, const float* z, int Nx,
+                     int Ny, int Nz, void* stream);
+int imhd_init_screwpinch(float* Q, float J0, float r_max_coeff, const float* x, const float* y,
+                         const float* z, int Nx, int Ny, int Nz, void* stream);
 
 /* ---- fused time step: the product hot path ---------------------------------------------------
  * One sweep Q^n -> Q^{n+1}: predictor, corrector, diffusion and every boundary pass of one
@@ -151,6 +160,29 @@ int imhd_ctx_init_grids(imhd_ctx* ctx, float x_min, float x_max, float y_min, fl
                         float z_min, float z_max);
 int imhd_ctx_init_screwpinch_stride(imhd_ctx* ctx, float J0);
 int imhd_ctx_init_cubic_bennett_vortex_m0(imhd_ctx* ctx, float k, float A);
+/* ---- string-keyed registry: the reference's planned plugin surface
+ * (include/on-device/utils/configurers.hpp:13-196; src/on-device/README.md:10-30).  Keys of the reference:
+ *   initializers   "screwpinch" {J0, r_max_coeff}, "screwpinch-stride" {J0}, "cubic-bennett-vortex" {}
+ *   correctors     "fluidadvancelocal-nodiff"
+ *   predictors     "corrector_advance-tp_nodiff", "corrector_advance-stride_nodiff"
+ *   fluid BCs      "pcrw-xy_pbc-z"          predictor BCs  "pbc-z"
+ * plus, in the slots it leaves open: "cubic-bennett-vortex-m0" {k, A}, "zpinch" {r_max_coeff},
+ * "fluidadvancelocal" / "corrector_advance-stride" (the with-diffusion loop of main.cu).
+ * Unknown keys fail with the reference's messages ("Unknown simulation type: ...") in imhd_last_error(). */
+#define IMHD_REG_INITIALIZER 0
+#define IMHD_REG_CORRECTOR 1
+#define IMHD_REG_PREDICTOR 2
+#define IMHD_REG_FLUID_BCS 3
+#define IMHD_REG_PREDICTOR_BCS 4
+int imhd_registry_count(int kind);
+const char* imhd_registry_name(int kind, int index);
+int imhd_registry_initializer_nparams(const char* sim_type); /* -1: unknown key */
+/* SimulationInitializer::initialize (configurers.hpp:32-39): run the named IC kernel on the context's state. */
+int imhd_ctx_initialize(imhd_ctx* ctx, const char* sim_type, const float* params, int nparams);
+/* Resolve a (corrector, predictor, fluid BCs, predictor BCs) selection to IMHD_PATH_A / IMHD_PATH_B for
+ * imhd_ctx_prime; bundles from different time loops do not mix. */
+int imhd_registry_resolve_path(const char* corrector, const char* predictor, const char* fluid_bcs,
+                               const char* predictor_bcs, int* path);
 /* Upload a host state (8*Nx*Ny*Nz floats, IDX3D) instead of running an IC kernel. */
 int imhd_ctx_set_state(imhd_ctx* ctx, const float* host_Q);
 /* Grid spacing for a state uploaded with imhd_ctx_set_state (imhd_ctx_init_grids sets it too). */

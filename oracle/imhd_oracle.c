@@ -483,3 +483,89 @@ void oracle_cubic_bennett_vortex_m0(float* Q, float kw, float A, const float* gx
                 }
             }
 }
+
+/* initialize_od.cu:59-130 -- the z-invariant cubic Bennett vortex (commented out in no_diffusion.cu:170) */
+void oracle_cubic_bennett_vortex(float* Q, const float* gx, const float* gy, const float* gz, int Nx, int Ny, int Nz) {
+    (void)gz;
+    dims_t dd = {Nx, Ny, Nz, (size_t)Nx * Ny * Nz};
+    const size_t cube = dd.cube;
+    const float r_pinch = (float)(0.25 * sqrtf((float)(sq(gx[Nx - 1]) + sq(gy[Ny - 1])))); /* :71 */
+    const float Br = 0.0f;
+    for (int k = 0; k < Nz; ++k)
+        for (int i = 0; i < Nx; ++i)
+            for (int j = 0; j < Ny; ++j) {
+                const size_t l = IDX(&dd, i, j, k);
+                const float xt = gx[i], yt = gy[j];
+                const float phi = sqrtf((float)(sq(xt) + sq(yt)));
+                vacuum_cell(Q, l, cube);
+                if (phi < r_pinch) {
+                    const float Btheta = (float)(-(pow(phi, 3) - 3 * sq(phi) - 6 * phi + 6 * (phi + 1) * logf(phi + 1)) /
+                                                 (2 * phi * (phi + 1))); /* :101 */
+                    const float p = (float)pow(phi, 3);                   /* :103 */
+                    Q[l] = 1.0f;
+                    Q[l + MZ * cube] = (float)(sq(phi) / sq(phi + 1));
+                    Q[l + BX * cube] = Br * xt - Btheta * yt / phi;
+                    Q[l + BY * cube] = Br * yt + Btheta * xt / phi;
+                    Q[l + EN * cube] = total_energy(Q, l, cube, p);
+                }
+            }
+}
+
+/* initialize_od.cu:347-424 */
+void oracle_zpinch(float* Q, float r_max_coeff, const float* gx, const float* gy, const float* gz, int Nx, int Ny, int Nz) {
+    (void)gz;
+    dims_t dd = {Nx, Ny, Nz, (size_t)Nx * Ny * Nz};
+    const size_t cube = dd.cube;
+    const float r_pinch = r_max_coeff * sqrtf((float)(sq(gx[Nx - 1]) + sq(gy[Ny - 1]))); /* :359, fp32 product */
+    const float Br = 0.0f;
+    for (int k = 0; k < Nz; ++k)
+        for (int i = 0; i < Nx; ++i)
+            for (int j = 0; j < Ny; ++j) {
+                const size_t l = IDX(&dd, i, j, k);
+                const float x = gx[i], y = gy[j];
+                const float r = sqrtf((float)(sq(x) + sq(y)));
+                vacuum_cell(Q, l, cube);
+                if (r < r_pinch) {
+                    const float Btheta = (float)(0.5 * (r + 0.5 * pow(r, 3) / sq(r_pinch))); /* :394 */
+                    const float p = (float)(1 + 0.5 * (0.5 * sq(r) / sq(r_pinch) + 0.375 * pow(r, 4) / pow(r_pinch, 4) -
+                                                       (1.0 / 12.0) * pow(r, 6) / pow(r_pinch, 6))); /* :398 */
+                    Q[l] = 1.0f;
+                    Q[l + MZ * cube] = (float)(1 + sq(r) / sq(r_pinch));
+                    Q[l + BX * cube] = Br * x - Btheta * y / r;
+                    Q[l + BY * cube] = Br * y + Btheta * x / r;
+                    Q[l + EN * cube] = total_energy(Q, l, cube, p);
+                }
+            }
+}
+
+/* initialize_od.cu:207-267 -- one thread per cell; outside the pinch ONLY rho (= 0.1) is written, the other seven
+ * variables keep whatever the buffer held (the reference never clears its cudaMalloc) */
+void oracle_screwpinch(float* Q, float J0, float r_max_coeff, const float* gx, const float* gy, const float* gz,
+                       int Nx, int Ny, int Nz) {
+    (void)gz;
+    dims_t dd = {Nx, Ny, Nz, (size_t)Nx * Ny * Nz};
+    const size_t cube = dd.cube;
+    const float r_pinch = r_max_coeff * sqrtf((float)(sq(gx[Nx - 1]) + sq(gy[Ny - 1]))); /* :219 */
+    const float Jr = 0.0f, Jphi = 0.0f, Br = 0.0f, B0 = 1.0f;
+    for (int k = 0; k < Nz; ++k)
+        for (int i = 0; i < Nx; ++i)
+            for (int j = 0; j < Ny; ++j) {
+                const size_t l = IDX(&dd, i, j, k);
+                const float x = gx[i], y = gy[j];
+                const float r = sqrtf((float)(sq(x) + sq(y)));
+                Q[l] = 0.1f; /* :237 */
+                if (r < r_pinch) {
+                    const float Btheta = (float)(0.5 * J0 * r * (1.0 - 0.5 * sq(r) / sq(r_pinch))); /* :243 */
+                    const float p = (float)(-0.25 * (sq(J0) / pow(r_pinch, 4)) *
+                                            (pow(r, 6) / 6.0 - 0.75 * sq(r_pinch) * pow(r, 4) + pow(r_pinch, 4) * sq(r))); /* :246 */
+                    Q[l] = 1.0f;
+                    Q[l + MX * cube] = Jr * x - Jphi * y / r;
+                    Q[l + MY * cube] = Jr * y + Jphi * x / r;
+                    Q[l + MZ * cube] = (float)(J0 * (1 - sq(r) / sq(r_pinch)));
+                    Q[l + BX * cube] = Br * x - Btheta * y / r;
+                    Q[l + BY * cube] = Br * y + Btheta * x / r;
+                    Q[l + BZ * cube] = B0;
+                    Q[l + EN * cube] = total_energy(Q, l, cube, p);
+                }
+            }
+}

@@ -81,6 +81,9 @@ class Oracle(_Lib):
         s("oracle_init_grids", [_p, _p, _p] + [_f] * 6 + dims)
         s("oracle_screwpinch_stride", [_p, _f, _p, _p, _p] + dims)
         s("oracle_cubic_bennett_vortex_m0", [_p, _f, _f, _p, _p, _p] + dims)
+        s("oracle_cubic_bennett_vortex", [_p, _p, _p, _p] + dims)
+        s("oracle_zpinch", [_p, _f, _p, _p, _p] + dims)
+        s("oracle_screwpinch", [_p, _f, _f, _p, _p, _p] + dims)
 
     # Q arrays have shape (8, Nz, Nx, Ny)
     @staticmethod
@@ -101,6 +104,22 @@ class Oracle(_Lib):
     def cubic_bennett_vortex_m0(self, k, A, x, y, z):
         Q = np.empty((8, len(z), len(x), len(y)), np.float32)
         self.lib.oracle_cubic_bennett_vortex_m0(_ptr(Q), k, A, _ptr(x), _ptr(y), _ptr(z), len(x), len(y), len(z))
+        return Q
+
+    def cubic_bennett_vortex(self, x, y, z):
+        Q = np.empty((8, len(z), len(x), len(y)), np.float32)
+        self.lib.oracle_cubic_bennett_vortex(_ptr(Q), _ptr(x), _ptr(y), _ptr(z), len(x), len(y), len(z))
+        return Q
+
+    def zpinch(self, r_max_coeff, x, y, z):
+        Q = np.empty((8, len(z), len(x), len(y)), np.float32)
+        self.lib.oracle_zpinch(_ptr(Q), r_max_coeff, _ptr(x), _ptr(y), _ptr(z), len(x), len(y), len(z))
+        return Q
+
+    def screwpinch(self, J0, r_max_coeff, x, y, z, prefill=None):
+        """``prefill``: what the buffer held before (only rho is written outside the pinch)."""
+        Q = np.zeros((8, len(z), len(x), len(y)), np.float32) if prefill is None else prefill.copy()
+        self.lib.oracle_screwpinch(_ptr(Q), J0, r_max_coeff, _ptr(x), _ptr(y), _ptr(z), len(x), len(y), len(z))
         return Q
 
     def predictor(self, Q, Qint, path, D, dt, dx, dy, dz):
@@ -156,6 +175,9 @@ class Reference(_Lib):
         s("ref_init_grids", [_p, _p, _p] + [_f] * 6 + dims)
         s("ref_screwpinch_stride", [_p, _f, _p, _p, _p] + dims + [_i])
         s("ref_cubic_bennett_vortex_m0", [_p, _f, _f, _p, _p, _p] + dims + [_i])
+        s("ref_cubic_bennett_vortex", [_p, _p, _p, _p] + dims + [_i])
+        s("ref_zpinch", [_p, _f, _p, _p, _p] + dims + [_i])
+        s("ref_screwpinch", [_p, _f, _f, _p, _p, _p] + dims + [_i])
         s("ref_wall_bcs_leftright", [_p] + dims)
         s("ref_wall_bcs_topbottom", [_p] + dims)
         s("ref_pbcs", [_p] + dims)
@@ -186,6 +208,21 @@ class Reference(_Lib):
     def cubic_bennett_vortex_m0(self, k, A, x, y, z):
         Q = np.empty((8, len(z), len(x), len(y)), np.float32)
         self.lib.ref_cubic_bennett_vortex_m0(_ptr(Q), k, A, _ptr(x), _ptr(y), _ptr(z), len(x), len(y), len(z), self.T)
+        return Q
+
+    def cubic_bennett_vortex(self, x, y, z):
+        Q = np.empty((8, len(z), len(x), len(y)), np.float32)
+        self.lib.ref_cubic_bennett_vortex(_ptr(Q), _ptr(x), _ptr(y), _ptr(z), len(x), len(y), len(z), self.T)
+        return Q
+
+    def zpinch(self, r_max_coeff, x, y, z):
+        Q = np.empty((8, len(z), len(x), len(y)), np.float32)
+        self.lib.ref_zpinch(_ptr(Q), r_max_coeff, _ptr(x), _ptr(y), _ptr(z), len(x), len(y), len(z), self.T)
+        return Q
+
+    def screwpinch(self, J0, r_max_coeff, x, y, z, prefill=None):
+        Q = np.zeros((8, len(z), len(x), len(y)), np.float32) if prefill is None else prefill.copy()
+        self.lib.ref_screwpinch(_ptr(Q), J0, r_max_coeff, _ptr(x), _ptr(y), _ptr(z), len(x), len(y), len(z), self.T)
         return Q
 
     def predictor(self, Q, Qint, path, D, dt, dx, dy, dz, full=False):
@@ -251,6 +288,7 @@ class ReferenceGPU(_Lib):
                            ("refgpu_pathA_steps", [_p, _p, _i, _f, _f, _f, _f] + dims + [_p, _p]),
                            ("refgpu_pathB_prime", [_p, _p, _f, _f, _f, _f, _f] + dims + [_p]),
                            ("refgpu_pathB_steps", [_p, _p, _i, _f, _f, _f, _f, _f] + dims + [_p, _p]),
+                           ("refgpu_init", [_i, _p, _f, _f, _p, _p, _p] + dims),
                            ("refgpu_covers", [_p] + dims), ("refgpu_num_sms", [])):
             fn = getattr(self.lib, name)
             fn.argtypes, fn.restype = args, _i
@@ -258,6 +296,14 @@ class ReferenceGPU(_Lib):
     @staticmethod
     def _geom(g):
         return (C.c_int * 8)(*[int(v) for v in g])
+
+    IC_IDS = {"screwpinch-stride": 0, "cubic-bennett-vortex-m0": 1, "cubic-bennett-vortex": 2, "zpinch": 3,
+              "screwpinch": 4}
+
+    def init(self, ic, Qptr, a, b, xptr, yptr, zptr, dims):
+        rc = self.lib.refgpu_init(self.IC_IDS[ic], Qptr, a, b, xptr, yptr, zptr, *dims)
+        if rc:
+            raise RuntimeError(f"reference GPU IC kernel failed: cudaError {rc}")
 
     def covers(self, g, Nx, Ny, Nz):
         return bool(self.lib.refgpu_covers(self._geom(g), Nx, Ny, Nz))

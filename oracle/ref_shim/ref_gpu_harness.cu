@@ -131,6 +131,23 @@ int refgpu_covers(const int* g, int Nx, int Ny, int Nz) {
            (long long)o.grid_cells.z * o.block.z >= Nz;
 }
 
+// ic: 0 ScrewPinchStride(a=J0) 1 CubicBennettVortex_m0(a=k,b=A) 2 CubicBennettVortex 3 ZPinch(a=r_max_coeff)
+//     4 ScrewPinch(a=J0,b=r_max_coeff); launch geometry of no_diffusion.cu:127-131 (8x8x8 blocks) sized to the domain
+int refgpu_init(int ic, float* Q, float a, float b, const float* x, const float* y, const float* z, int Nx, int Ny,
+                int Nz) {
+    dim3 block(8, 8, 8), grid(cdiv(Nx, 8), cdiv(Ny, 8), cdiv(Nz, 8));
+    switch (ic) {
+        case 0: ScrewPinchStride<<<grid, block>>>(Q, a, x, y, z, Nx, Ny, Nz); break;
+        case 1: CubicBennettVortex_m0<<<grid, block>>>(Q, a, b, x, y, z, Nx, Ny, Nz); break;
+        case 2: CubicBennettVortex<<<grid, block>>>(Q, x, y, z, Nx, Ny, Nz); break;
+        case 3: ZPinch<<<grid, block>>>(Q, a, x, y, z, Nx, Ny, Nz); break;
+        case 4: ScrewPinch<<<grid, block>>>(Q, a, b, x, y, z, Nx, Ny, Nz); break;
+        default: return -1;
+    }
+    cudaDeviceSynchronize();
+    return (int)cudaGetLastError();
+}
+
 int refgpu_pathA_prime(float* Q, float* Qint, float dt, float dx, float dy, float dz, int Nx, int Ny, int Nz,
                        const int* g) {
     Geo o = make_geo(g, Nx, Ny, Nz);

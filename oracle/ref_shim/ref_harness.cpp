@@ -95,6 +95,21 @@ void ref_cubic_bennett_vortex_m0(float* Q, float kwave, float A, const float* x,
     launch_stride(T, [&] { CubicBennettVortex_m0(Q, kwave, A, x, y, z, Nx, Ny, Nz); });
 }
 
+// the three initial conditions the shipped drivers keep commented out (no_diffusion.cu:169-171)
+void ref_cubic_bennett_vortex(float* Q, const float* x, const float* y, const float* z, int Nx, int Ny, int Nz, int T) {
+    launch_stride(T, [&] { CubicBennettVortex(Q, x, y, z, Nx, Ny, Nz); });
+}
+
+void ref_zpinch(float* Q, float r_max_coeff, const float* x, const float* y, const float* z, int Nx, int Ny, int Nz,
+                int T) {
+    launch_stride(T, [&] { ZPinch(Q, r_max_coeff, x, y, z, Nx, Ny, Nz); });
+}
+
+void ref_screwpinch(float* Q, float J0, float r_max_coeff, const float* x, const float* y, const float* z, int Nx,
+                    int Ny, int Nz, int T) {
+    launch_cells(Nx, Ny, Nz, T, [&] { ScrewPinch(Q, J0, r_max_coeff, x, y, z, Nx, Ny, Nz); });
+}
+
 // ---- Path A granular kernels ------------------------------------------------
 void ref_wall_bcs_leftright(float* Q, int Nx, int Ny, int Nz) {
     // <<<(S,1,S),(bx,1,bz)>>> : (x,z) threads (no_diffusion.cu:174)

@@ -71,3 +71,30 @@ def test_bad_arguments_are_rejected(imhd):
     s = imhd.ops.make_slab(16, 16, 16, 0, 0.0, 1e-4, 0.1, 0.1, 0.1, k0=4, nzl=4, ghosts=0)
     assert lib.imhd_step_fused(None, None, None, None, None, C.byref(s), None) == imhd._lib.E_INVALID
     assert "ghosts" in lib.imhd_last_error().decode()
+
+
+# ---- string-keyed registry (include/on-device/utils/configurers.hpp); pure host logic, no GPU needed ----------
+def test_registry_lists_the_reference_keys(imhd):
+    ops = imhd.ops
+    assert ops.registry_names(ops.REG_INITIALIZER)[:3] == ["screwpinch", "screwpinch-stride", "cubic-bennett-vortex"]
+    assert "fluidadvancelocal-nodiff" in ops.registry_names(ops.REG_CORRECTOR)
+    assert {"corrector_advance-tp_nodiff", "corrector_advance-stride_nodiff"} <= set(ops.registry_names(ops.REG_PREDICTOR))
+    assert ops.registry_names(ops.REG_FLUID_BCS) == ["pcrw-xy_pbc-z"]
+    assert ops.registry_names(ops.REG_PREDICTOR_BCS) == ["pbc-z"]
+    L = imhd._lib.load()
+    assert L.imhd_registry_name(0, 99) is None and L.imhd_registry_count(17) == 0
+    assert L.imhd_registry_initializer_nparams(b"screwpinch") == 2
+    assert L.imhd_registry_initializer_nparams(b"orszag-tang") == -1
+
+
+def test_registry_resolves_bundles_to_a_time_loop(imhd):
+    ops = imhd.ops
+    assert ops.registry_resolve_path("fluidadvancelocal-nodiff", "corrector_advance-tp_nodiff") == 0
+    assert ops.registry_resolve_path("fluidadvancelocal-nodiff", "corrector_advance-stride_nodiff") == 0
+    assert ops.registry_resolve_path("fluidadvancelocal", "corrector_advance-stride") == 1
+    for args, msg in ((("nope", "corrector_advance-tp_nodiff"), "Unknown kernel bundle selected: nope"),
+                      (("fluidadvancelocal-nodiff", "nope"), "Unknown I.V. kernel bundle selection: nope"),
+                      (("fluidadvancelocal-nodiff", "corrector_advance-tp_nodiff", "all-pbc"), "Unknown bcs selected: all-pbc"),
+                      (("fluidadvancelocal", "corrector_advance-tp_nodiff"), "different time loops")):
+        with pytest.raises(imhd.ImhdError, match=msg):
+            ops.registry_resolve_path(*args)

@@ -72,3 +72,27 @@ def test_launcher_runs_the_drop_in_driver(tmp_path, O, oracle_mod, mode):
     O.steps(qo, io, path, nt - 1, D, om_dt, *d)
     fl = read_frame(data + f"fluidvars_{nt - 1}.h5", dims)
     assert (om.normalised_linf(fl, qo) <= 1e-5).all()
+
+
+def test_driver_selects_the_initial_condition_by_registry_key(tmp_path, O, oracle_mod):
+    """IMHD_IC=<configurers.hpp key>: same executable, another IC kernel (the reference needs a rebuild for that,
+    no_diffusion.cu:168-171)."""
+    om = oracle_mod
+    dims = (32, 28, 20)
+    data = str(tmp_path / "data") + "/"
+    os.makedirs(data)
+    inp = patched_input(tmp_path, "input.inp", Nt=5, Nx=dims[0], Ny=dims[1], Nz=dims[2], r_max_coeff=0.3)
+    run = [sys.executable, os.path.join(DRV, "simulation_launcher.py"), "nodiff", "--input", inp, "--data-dir", data]
+    out = subprocess.run(run, capture_output=True, text=True, env=dict(os.environ, IMHD_IC="zpinch", IMHD_OUTPUT_EVERY="4"))
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Initial condition: zpinch" in out.stdout
+    g = O.init_grids(BOUNDS, *dims)
+    d = tuple(float(om.grid_spacing(BOUNDS[2 * a], BOUNDS[2 * a + 1], n)) for a, n in enumerate(dims))
+    qo = O.zpinch(0.3, *g)  # r_max_coeff from argv slot 7
+    io = np.zeros_like(qo)
+    O.prime(qo, io, om.PATH_A, 0.0, 1e-4, *d)
+    assert np.array_equal(read_frame(data + "fluidvars_0.h5", dims), qo)
+    O.steps(qo, io, om.PATH_A, 4, 0.0, 1e-4, *d)
+    assert (om.normalised_linf(read_frame(data + "fluidvars_4.h5", dims), qo) <= 1e-5).all()
+    bad = subprocess.run(run, capture_output=True, text=True, env=dict(os.environ, IMHD_IC="orszag-tang"))
+    assert bad.returncode != 0 and "Unknown simulation type: orszag-tang" in bad.stdout + bad.stderr

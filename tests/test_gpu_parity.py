@@ -75,6 +75,56 @@ def test_bennett_vortex_ic(imhd, torch, O, oracle_mod):
     np.testing.assert_allclose(Q, Q0, rtol=0, atol=5e-7)
 
 
+@pytest.mark.parametrize("dims", [(40, 36, 20), (24, 18, 5)])
+def test_other_initial_conditions(imhd, torch, O, oracle_mod, dims):
+    """CubicBennettVortex, ZPinch, ScrewPinch (initialize_od.cu:59, 347, 207) against the oracle."""
+    g = O.init_grids(BOUNDS, *dims)
+    gx, gy, gz = imhd.ops.init_grids(BOUNDS, *dims)
+    for coeff in (0.25, 0.4):
+        assert bits_equal(imhd.ops.init_zpinch(coeff, gx, gy, gz).cpu().numpy(), O.zpinch(coeff, *g))
+        pre = random_state(*dims, seed=5)
+        Q = imhd.ops.init_screwpinch(1.0, coeff, gx, gy, gz, prefill=dev(torch, pre)).cpu().numpy()
+        assert bits_equal(Q, O.screwpinch(1.0, coeff, *g, prefill=pre))
+    # logf of CUDA and glibc may differ in the last bit
+    Q, Q0 = imhd.ops.init_cubic_bennett_vortex(gx, gy, gz).cpu().numpy(), O.cubic_bennett_vortex(*g)
+    assert np.array_equal(Q == 0, Q0 == 0)
+    np.testing.assert_allclose(Q, Q0, rtol=0, atol=5e-7)
+
+
+def test_registry_initializers_run_the_named_kernel(imhd, torch, O, oracle_mod):
+    dims = (24, 18, 6)
+    g = O.init_grids(BOUNDS, *dims)
+    want = {("screwpinch-stride", (1.0,)): O.screwpinch_stride(1.0, *g),
+            ("screwpinch", (1.0, 0.3)): O.screwpinch(1.0, 0.3, *g),  # the context clears the buffer first
+            ("zpinch", (0.25,)): O.zpinch(0.25, *g)}
+    with imhd.ops.Context(*dims) as ctx:
+        with pytest.raises(imhd.ImhdError, match="before imhd_ctx_init_grids"):
+            ctx.initialize("zpinch", 0.25)
+        ctx.init_grids(*BOUNDS)
+        for (key, params), Q0 in want.items():
+            ctx.initialize(key, *params)
+            assert bits_equal(ctx.get_state(), Q0), key
+        for key, params in (("cubic-bennett-vortex", ()), ("cubic-bennett-vortex-m0", (2.0, 0.5))):
+            ctx.initialize(key, *params)
+            Q0 = O.cubic_bennett_vortex(*g) if not params else O.cubic_bennett_vortex_m0(2.0, 0.5, *g)
+            np.testing.assert_allclose(ctx.get_state(), Q0, rtol=0, atol=5e-7)
+        with pytest.raises(imhd.ImhdError, match="Unknown simulation type: orszag-tang"):
+            ctx.initialize("orszag-tang")
+        with pytest.raises(imhd.ImhdError, match="takes 2 parameter"):
+            ctx.initialize("screwpinch", 1.0)
+        # a registry-selected job: keys -> path -> prime -> step
+        path = imhd.ops.registry_resolve_path("fluidadvancelocal", "corrector_advance-stride")
+        ctx.initialize("screwpinch-stride", 1.0)
+        ctx.prime(path, D_B, DT)
+        ctx.step(3)
+        Q = ctx.get_state()
+    d = tuple(float(oracle_mod.grid_spacing(BOUNDS[2 * a], BOUNDS[2 * a + 1], n)) for a, n in enumerate(dims))
+    Qo, Qi = O.screwpinch_stride(1.0, *g), np.zeros((8, dims[2], dims[0], dims[1]), np.float32)
+    O.prime(Qo, Qi, path, D_B, DT, *d)
+    O.steps(Qo, Qi, path, 3, D_B, DT, *d)
+    assert oracle_mod.normalised_linf(Q, Qo).max() <= 1e-6
+
+
 # ------------------------------------------------------------------------------------------------------
 # parity-granular operators: bit-exact
 # ------------------------------------------------------------------------------------------------------

@@ -100,3 +100,29 @@ def test_fused_c1_100_steps_vs_reference_kernels_on_the_same_gpu(imhd, torch, O,
     err = oracle_mod.normalised_linf(Qf, Qr)
     print(f"\nfused vs reference kernels on sm_100 (stock flags), C1 path {tag}, 100 steps: nLinf per variable {err}")
     assert err.max() <= TOL
+
+
+def test_initial_condition_kernels_vs_reference_kernels_on_the_gpu(imhd, torch, O, oracle_mod):
+    """All five IC kernels of initialize_od.cu, reference (nvcc sm_100, -fmad=false) vs ours, same device: here the
+    transcendental functions (logf, cosf) are the SAME libdevice code, so every one must match bit for bit."""
+    from conftest import BOUNDS
+
+    G = refgpu(oracle_mod, nofma=True)
+    dims = (40, 36, 20)
+    gx, gy, gz = imhd.ops.init_grids(BOUNDS, *dims)
+    pre = torch.from_numpy(random_state(*dims, seed=5)).cuda()
+    ours = {"screwpinch-stride": (imhd.ops.init_screwpinch_stride(1.0, gx, gy, gz), 1.0, 0.0),
+            "cubic-bennett-vortex-m0": (imhd.ops.init_cubic_bennett_vortex_m0(2.0, 0.5, gx, gy, gz), 2.0, 0.5),
+            "cubic-bennett-vortex": (imhd.ops.init_cubic_bennett_vortex(gx, gy, gz), 0.0, 0.0),
+            "zpinch": (imhd.ops.init_zpinch(0.3, gx, gy, gz), 0.3, 0.0),
+            "screwpinch": (imhd.ops.init_screwpinch(1.0, 0.3, gx, gy, gz, prefill=pre), 1.0, 0.3)}
+    for key, (Q, a, b) in ours.items():
+        Qr = pre.clone()
+        G.init(key, Qr.data_ptr(), a, b, gx.data_ptr(), gy.data_ptr(), gz.data_ptr(), dims)
+        torch.cuda.synchronize()
+        eq = bits_equal(Q.cpu().numpy(), Qr.cpu().numpy())
+        err = np.abs(Q.cpu().numpy().astype(np.float64) - Qr.cpu().numpy()).max()
+        print(f"\n{key}: bit-identical to the reference kernel on sm_100 = {eq} (max abs diff {err:.2e})")
+        assert err <= 5e-7, key
+        if key in ("screwpinch-stride", "zpinch", "screwpinch"):
+            assert eq, key

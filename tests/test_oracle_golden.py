@@ -155,3 +155,35 @@ def test_path_b_cell_sets(O, oracle_mod):
     for i in (0, -1):
         assert (Q[0, 0, i, :] == 1).all() and (Q[1:7, 0, i, :] == 0).all()
     assert bits_equal(Q[:, -1, -1, -1], Q[:, 0, -1, -1])
+
+
+# ------------------------------------------------------------------------------------------------------
+# the three initial conditions the shipped drivers keep commented out (initialize_od.cu:59, 207, 347)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dims", [(10, 8, 7), (24, 18, 5)])
+def test_other_initial_conditions_bit_exact_vs_reference_kernels(O, R, oracle_mod, dims):
+    from conftest import BOUNDS
+
+    g = O.init_grids(BOUNDS, *dims)
+    assert bits_equal(O.cubic_bennett_vortex(*g), R.cubic_bennett_vortex(*g))
+    for coeff in (0.25, 0.4):
+        assert bits_equal(O.zpinch(coeff, *g), R.zpinch(coeff, *g))
+        pre = random_state(*dims, seed=5)
+        a, b = O.screwpinch(1.0, coeff, *g, prefill=pre), R.screwpinch(1.0, coeff, *g, prefill=pre)
+        assert bits_equal(a, b)
+        # outside the pinch ScrewPinch writes rho = 0.1 only (initialize_od.cu:237): the other seven keep the prefill
+        outside = a[0] == np.float32(0.1)
+        assert outside.any() and (~outside).any()
+        assert bits_equal(a[1:][:, outside], pre[1:][:, outside])
+        assert np.all(a[0][~outside] == 1.0)
+
+
+def test_zpinch_and_bennett_are_z_invariant_equilibria(O, oracle_mod):
+    from conftest import BOUNDS
+
+    g = O.init_grids(BOUNDS, 20, 20, 6)
+    for Q in (O.zpinch(0.25, *g), O.cubic_bennett_vortex(*g)):
+        assert np.isfinite(Q).all()
+        assert all(bits_equal(Q[:, k], Q[:, 0]) for k in range(Q.shape[1]))
+        assert set(np.unique(Q[0])) == {np.float32(0.01), np.float32(1.0)}
+        assert not Q[1].any() and not Q[2].any() and not Q[6].any()  # no in-plane flow, no axial field
