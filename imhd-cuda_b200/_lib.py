@@ -27,6 +27,13 @@ class Slab(C.Structure):
     ]
 
 
+class Stability(C.Structure):
+    """``imhd_stability`` of include/imhd_b200.h."""
+
+    _fields_ = [("max_lhs", C.c_float), ("i", C.c_int), ("j", C.c_int), ("k", C.c_int),
+                ("violations", C.c_ulonglong), ("dt_new", C.c_float)]
+
+
 _f, _i, _p, _u64 = C.c_float, C.c_int, C.c_void_p, C.c_uint64
 _dims = [_i, _i, _i]
 _op = [_p, _p, _i, _f, _f, _f, _f, _f] + _dims + [_p]
@@ -48,6 +55,8 @@ SIGNATURES = {
     "imhd_init_screwpinch": (_i, [_p, _f, _f, _p, _p, _p] + _dims + [_p]),
     "imhd_step_fused": (_i, [_p, _p, _p, _p, _p, C.POINTER(Slab), _p]),
     "imhd_step_fused_planes": (_i, [_p, _p, _p, _p, _p, C.POINTER(Slab), _i, _i, _p]),
+    "imhd_stability_scan": (_i, [_p, C.POINTER(Slab), C.POINTER(Stability), _p]),
+    "imhd_ctx_stability": (_i, [_p, _f, C.POINTER(Stability)]),
     "imhd_wall_energy_fixed_point": (_f, [_f, _i]),
     "imhd_set_chunk": (None, [_i]),
     "imhd_set_kernel_variant": (None, [_i]),

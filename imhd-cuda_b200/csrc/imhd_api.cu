@@ -291,6 +291,15 @@ extern "C" int imhd_registry_resolve_path(const char* corrector, const char* pre
     return 0;
 }
 
+extern "C" int imhd_ctx_stability(imhd_ctx* c, float dt, imhd_stability* host_out) {
+    CTX_CHECK(c);
+    imhd_slab s;
+    memset(&s, 0, sizeof(s));
+    s.Nx = c->Nx; s.Ny = c->Ny; s.Nz = c->Nz; s.k0 = 0; s.nzl = c->Nz; s.ghosts = 0;
+    s.dt = dt; s.dx = c->dx; s.dy = c->dy; s.dz = c->dz;
+    return imhd_stability_scan(c->buf[c->cur], &s, host_out, c->stream);
+}
+
 extern "C" int imhd_ctx_set_state(imhd_ctx* c, const float* host_Q) {
     CTX_CHECK(c);
     if (!host_Q) { set_error("imhd_ctx_set_state: null host buffer"); return IMHD_E_INVALID; }

@@ -6,7 +6,7 @@
 // per-step blocking D2H + fork of mpirun/PHDF5 (main.cu:216-226) is an asynchronous snapshot -> D2H -> writer thread.
 // The execution-configuration arguments (block dims, SM multipliers) are accepted and ignored: the library picks its
 // own tiling.  The writer/attribute/grid binary names and num_proc are accepted and unused (output is in-process);
-// eigen_bin_name other than "none" prints a notice (the Eigen CFL scanner is out of scope).
+// eigen_bin_name other than "none" runs the CFL scan on the device (imhd_ctx_stability) and prints the scanner's report.
 // Optional environment: IMHD_OUTPUT_EVERY=n (default 1 = the reference's behaviour), IMHD_DEVICE=d,
 // IMHD_IC=<registry key>[:p0[,p1]] selects the initial condition by the reference's registry key
 // (include/on-device/utils/configurers.hpp:21-29) instead of the one each shipped driver hard-codes; parameters left
@@ -93,7 +93,14 @@ int main(int argc, char* argv[]) {
     printf("Writing initial conditions and grid to %s\n", path_to_data.c_str());
     CHECK(imhd_ctx_write_frame(ctx, path_to_data.c_str(), 0));
     CHECK(imhd_ctx_write_grid(ctx, path_to_data.c_str()));
-    if (eigen_bin_name != "none") printf("note: CFL scan '%s' is not part of this build; continuing without it\n", eigen_bin_name.c_str());
+    if (eigen_bin_name != "none") {
+        // the reference forks its host scanner here (no_diffusion.cu:259-276, compute_stability.cpp); same report, on the device
+        imhd_stability st;
+        CHECK(imhd_ctx_stability(ctx, dt, &st));
+        printf("Old timestep: %g\nLargest violation: %g at (i,j,k) = (%d,%d,%d)\nNew timestep: %g\n"
+               "Total number of stability violations detected: %llu\n",
+               dt, st.max_lhs, st.i, st.j, st.k, st.dt_new, st.violations);
+    }
 
     const auto t0 = std::chrono::steady_clock::now();
     for (int it = 1; it < Nt; it++) {

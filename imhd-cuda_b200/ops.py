@@ -147,6 +147,16 @@ def registry_resolve_path(corrector: str, predictor: str, fluid_bcs: str = "pcrw
     return path.value
 
 
+# ---- CFL / stability scan (src/on-device/utils/compute_stability.cpp) -----------------------------------
+def stability_scan(Q, slab: Slab) -> dict:
+    """Scan the owned planes of a slab state on its device; returns max_lhs, argmax (i, j, k) in global indices,
+    violations and the reference's dt proposal.  Synchronises."""
+    out = _lib.Stability()
+    check(_lib.load().imhd_stability_scan(_dev(Q), C.byref(slab), C.byref(out), _stream()))
+    return {"max_lhs": out.max_lhs, "argmax_ijk": (out.i, out.j, out.k), "violations": int(out.violations),
+            "dt_new": out.dt_new}
+
+
 # ---- fused step -----------------------------------------------------------------------------------
 def make_slab(Nx, Ny, Nz, path, D, dt, dx, dy, dz, k0=0, nzl=None, ghosts=0, corner_e=0.0) -> Slab:
     return Slab(Nx, Ny, Nz, k0, Nz if nzl is None else nzl, ghosts, path, D, dt, dx, dy, dz, corner_e)
@@ -236,6 +246,12 @@ class Context:
         """SimulationInitializer::initialize (configurers.hpp:32-39): IC kernel by registry key."""
         arr = (C.c_float * max(1, len(params)))(*params)
         check(self.L.imhd_ctx_initialize(self.h, sim_type.encode(), arr, len(params)))
+
+    def stability(self, dt: float) -> dict:
+        out = _lib.Stability()
+        check(self.L.imhd_ctx_stability(self.h, dt, C.byref(out)))
+        return {"max_lhs": out.max_lhs, "argmax_ijk": (out.i, out.j, out.k), "violations": int(out.violations),
+                "dt_new": out.dt_new}
 
     def set_state(self, Q: np.ndarray):
         Q = np.ascontiguousarray(Q, dtype=np.float32)

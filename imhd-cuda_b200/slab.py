@@ -15,8 +15,10 @@ Per time step and rank (ring neighbours, periodic in z):
      and lands in rank 0's OWNED plane 0.
 Steps 1 and 3 run on a side stream underneath the interior launch of step 2 (the predictor planes of the next
 step only need the new end planes), so the interior never waits for a message.
-No reduction is needed anywhere (the reference has no global dt control).  Results are bit-identical for
+The time step needs no reduction (the reference has no global dt control).  Results are bit-identical for
 every number of ranks: each value is computed by the same device function from the same inputs.
+The optional CFL scan (``SlabSolver.stability``, replacing the reference's forked host scanner) is the one place
+with a reduction: max of the per-slab maxima, sum of the violation counts, one small all-gather.
 
 The communication layer is injected (``comm``) so the host logic runs under gloo on CPU in the tests.
 """
@@ -97,6 +99,29 @@ class TorchComm:
                    d.P2POp(d.irecv, recv_from_down, down, self.group), d.P2POp(d.irecv, recv_from_up, up, self.group)]
         for req in d.batch_isend_irecv(ops):
             req.wait()
+
+    def allgather_row(self, row):
+        """Every rank contributes one row of numbers; returns the rows of all ranks in rank order (float64)."""
+        import torch
+
+        dev = "cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu"
+        mine = torch.tensor(row, dtype=torch.float64, device=dev)
+        out = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(out, mine, group=self.group)
+        return [o.tolist() for o in out]
+
+
+def combine_stability(rows, dt, alpha=0.1):
+    """Per-slab scan results [max_lhs, i, j, k, violations] in rank (= ascending k) order -> the scan of the whole
+    domain: the largest LHS (the first one in the reference's scan order k, i, j on ties), the total number of
+    violations and dt_new = alpha * dt / max (src/on-device/utils/compute_stability.cpp:139-141)."""
+    best = None
+    for r in rows:
+        if best is None or r[0] > best[0]:
+            best = r
+    mx = float(best[0])
+    return {"max_lhs": mx, "argmax_ijk": (int(best[1]), int(best[2]), int(best[3])),
+            "violations": int(sum(int(r[4]) for r in rows)), "dt_new": alpha * dt / mx if mx > 0 else 0.0}
 
 
 class SlabSolver:
@@ -186,6 +211,19 @@ class SlabSolver:
         if L.rank < L.world - 1:
             Q[:, L.nzl + 1].copy_(self.recv_hi)
 
+    # ---- CFL scan ---------------------------------------------------------------------------------------
+    def stability(self, dt=None):
+        """Stability criterion of the current state over the WHOLE domain (every rank returns the same dict)."""
+        D, dt0, dx, dy, dz = self.params
+        dt = dt0 if dt is None else dt
+        L, c = self.layout, self.compute
+        slab = self.slab if dt == dt0 else c.make_slab(self.Nx, self.Ny, self.Nz, self.path, D, dt, dx, dy, dz, k0=L.k0,
+                                                       nzl=L.nzl, ghosts=1, corner_e=self.corner_e)
+        r = c.stability_scan(self.Q[self.cur], slab)
+        row = [r["max_lhs"], *r["argmax_ijk"], r["violations"]]
+        rows = [row] if self.comm is None or L.world == 1 else self.comm.allgather_row(row)
+        return combine_stability(rows, dt)
+
     # ---- time loop --------------------------------------------------------------------------------------
     def step(self, nsteps=1):
         L, c, t = self.layout, self.compute, self.torch
@@ -217,4 +255,4 @@ class SlabSolver:
             self.cur = 1 - self.cur
 
 
-__all__ = ["SlabLayout", "SlabSolver", "TorchComm", "PATH_A", "PATH_B"]
+__all__ = ["SlabLayout", "SlabSolver", "TorchComm", "combine_stability", "PATH_A", "PATH_B"]

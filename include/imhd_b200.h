@@ -138,6 +138,20 @@ int imhd_step_fused(const float* Qin, float* Qout, const float* qint_lo, const f
 int imhd_step_fused_planes(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
                            const float* qint_wrap, const imhd_slab* s, int kfrom, int kto, void* stream);
 
+/* ---- CFL / stability scan (replaces the forked host scanner src/on-device/utils/compute_stability.cpp) ----------
+ * One device pass over the owned planes of a slab state (same Q / imhd_slab conventions as imhd_step_fused; dt, dx,
+ * dy, dz from the slab): LHS = (dt/dx)|l_x| + (dt/dy)|l_y| + (dt/dz)|l_z| per cell (:157-163) with |l_d| the
+ * spectral radius of the ideal-MHD flux Jacobian in closed form (|u_d| + fast magnetosonic speed for a physical
+ * state) instead of Eigen on three 8x8 matrices (:165-181).  Synchronises the stream and fills host_out.
+ * Across slabs: max over max_lhs (ties: smallest k), sum over violations (imhd-cuda_b200/slab.py). */
+typedef struct imhd_stability {
+    float max_lhs;                 /* largest LHS among the scanned cells (0 if none is positive and finite) */
+    int i, j, k;                   /* its cell, global indices; first in the reference's scan order (k, i, j) */
+    unsigned long long violations; /* cells with LHS >= 1 (:120-121) */
+    float dt_new;                  /* 0.1 * dt / max_lhs: the reference's proposal (:139-141); 0 if max_lhs == 0 */
+} imhd_stability;
+int imhd_stability_scan(const float* Q, const imhd_slab* s, imhd_stability* host_out, void* stream);
+
 /* e <- p(e,0,0)/(gamma-1) iterated to its fixed point (lib/on-device/kernels_fluidbcs.cu:173,187; every
  * x-thread of the reference launch re-applies it).  Scalar host helper, identity when e == 0. */
 float imhd_wall_energy_fixed_point(float e, int max_iter);
@@ -197,6 +211,8 @@ int imhd_ctx_step_granular(imhd_ctx* ctx, int nsteps);
 /* Copy the current state / intermediate state / grids to host memory (synchronises). */
 int imhd_ctx_get_state(imhd_ctx* ctx, float* host_Q);
 int imhd_ctx_get_grids(imhd_ctx* ctx, float* x, float* y, float* z);
+/* imhd_stability_scan of the context's current state with its spacing and the given dt. */
+int imhd_ctx_stability(imhd_ctx* ctx, float dt, imhd_stability* host_out);
 /* Device pointer of the current state (valid until the next step call). */
 float* imhd_ctx_device_state(imhd_ctx* ctx);
 void* imhd_ctx_stream(imhd_ctx* ctx);

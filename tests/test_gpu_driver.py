@@ -94,5 +94,19 @@ def test_driver_selects_the_initial_condition_by_registry_key(tmp_path, O, oracl
     assert np.array_equal(read_frame(data + "fluidvars_0.h5", dims), qo)
     O.steps(qo, io, om.PATH_A, 4, 0.0, 1e-4, *d)
     assert (om.normalised_linf(read_frame(data + "fluidvars_4.h5", dims), qo) <= 1e-5).all()
+    # eigen_bin_name != none: the CFL report the reference's forked scanner prints (compute_stability.cpp:143-147)
+    inp2 = patched_input(tmp_path, "input.inp", Nt=2, Nx=dims[0], Ny=dims[1], Nz=dims[2], eigen_bin_name="on-device/utils/fj_evs_compute")
+    rep = subprocess.run([*run[:4], inp2, *run[5:]], capture_output=True, text=True, env=dict(os.environ, IMHD_IC="zpinch:0.3"))
+    assert rep.returncode == 0, rep.stdout + rep.stderr
+    import re
+    from oracle import stability as st
+    m = re.search(r"Largest violation: (\S+) at \(i,j,k\) = \((\d+),(\d+),(\d+)\)\nNew timestep: (\S+)\nTotal number of stability violations detected: (\d+)", rep.stdout)
+    assert m, rep.stdout
+    q0 = O.zpinch(0.3, *g)
+    i0 = np.zeros_like(q0)
+    O.prime(q0, i0, om.PATH_A, 0.0, 1e-4, *d)
+    want = st.scan(st.wave_speed_lhs(q0, 1e-4, *d), 1e-4)
+    assert float(m.group(1)) == pytest.approx(want["max_lhs"], rel=1e-5) and int(m.group(6)) == want["violations"]
+    assert float(m.group(5)) == pytest.approx(want["dt_new"], rel=1e-5)
     bad = subprocess.run(run, capture_output=True, text=True, env=dict(os.environ, IMHD_IC="orszag-tang"))
     assert bad.returncode != 0 and "Unknown simulation type: orszag-tang" in bad.stdout + bad.stderr

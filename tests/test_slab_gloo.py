@@ -50,6 +50,11 @@ class StubCompute:
         out.fill_(1000.0 + k)
         return out
 
+    def stability_scan(self, Q, slab):
+        # rank-dependent fake scan: the maximum sits in the LAST slab, ties with the one before it
+        top = 0.25 * min(slab.k0 // slab.nzl + 1, slab.Nz // slab.nzl - 1) if slab.Nz // slab.nzl > 2 else 0.25 * (slab.k0 // slab.nzl + 1)
+        return {"max_lhs": top, "argmax_ijk": (1, 2, slab.k0 + 1), "violations": slab.k0 + 3, "dt_new": 0.0}
+
     def step_fused_planes(self, Qin, Qout, lo, hi, wrap, slab, kfrom, kto):
         assert (kfrom, kto) == (slab.k0, slab.k0 + slab.nzl)  # CPU path: no overlap, one launch over the owned planes
         self.seen.append((float(lo[0, 0, 0]), float(hi[0, 0, 0]), None if wrap is None else float(wrap[0, 0, 0])))
@@ -72,7 +77,8 @@ def _worker(rank, world, path, port, q):
         s.load_global(glob)
         s.step(2)
         Q = s.Q[s.cur]
-        res = {"rank": rank, "seen": comp.seen, "owned": Q[0, 1:-1, 0, 0].tolist(), "lo_ghost": float(Q[0, 0, 0, 0]),
+        stab = s.stability()
+        res = {"rank": rank, "stab": stab, "seen": comp.seen, "owned": Q[0, 1:-1, 0, 0].tolist(), "lo_ghost": float(Q[0, 0, 0, 0]),
                "hi_ghost": float(Q[0, -1, 0, 0]), "k0": L.k0, "k1": L.k1}
         q.put(res)
     finally:
@@ -91,6 +97,13 @@ def test_ring_exchange_under_gloo(world, path):
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     Nz = 6 * world
+    # CFL scan: every rank holds the same combined result; on a tie the first slab in scan order (smallest k) wins
+    tops = [0.25 * (min(rk + 1, world - 1) if world > 2 else rk + 1) for rk in range(world)]
+    first = tops.index(max(tops))
+    want = {"max_lhs": max(tops), "argmax_ijk": (1, 2, 6 * first + 1), "violations": sum(6 * rk + 3 for rk in range(world)),
+            "dt_new": 0.1 * 1e-4 / max(tops)}
+    for r in res:
+        assert r["stab"] == pytest.approx(want), r["stab"]
     for r in res:
         k0, k1, rank = r["k0"], r["k1"], r["rank"]
         # predictor planes handed to the fused step: lo = Qint(k0-1) (own Qint(0) on rank 0), hi = Qint(k1) (Qint(0) on the last rank),
