@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libimhd_b200.so")
+# IMHD_B200_LIB: load another build of the same ABI (kernel experiments, tools/experiments/)
+LIB_PATH = os.environ.get("IMHD_B200_LIB") or os.path.join(PKG_DIR, "libimhd_b200.so")
 
 PATH_A, PATH_B = 0, 1
 E_INVALID, E_STATE, E_IO = 10001, 10002, 10003
