@@ -50,6 +50,7 @@ struct FusedArgs {
     int hi_plane;
     int chunk;          // owned planes per z-chunk
     int ntile_i, ntile_j;
+    int jstrip;         // remainder-strip kernel only: j of its first thread row
     float corner_e;     // path B: fixed-point wall energy of column (Nx-1,Ny-1) (B-8)
     Params P;
 };
@@ -111,9 +112,9 @@ __device__ __forceinline__ void qint_cell(const float c[8], const float xp[8], c
 // Corrector at one cell (fast recipe).  q = Q(i,j,k); c, xm, ym, zm = Qint at the cell and at
 // i-1, j-1, k-1; xp, yp, zp = Qint at i+1, j+1, k+1 (path B diffusion only).
 // kernels_od.cu:378-522 / :120-345, LaxWendroffAdv*Local :1206-1332, quirks B-4, B-5, B-6.
-// Must be called by all 32 lanes of a warp whose lanes hold consecutive j (it shuffles).
+// Must be called by all 32 lanes of a warp whose lanes hold consecutive j (LANES_I: consecutive i); it shuffles.
 // -----------------------------------------------------------------------------------------------
-template <int PATH>
+template <int PATH, bool LANES_I = false>
 __device__ __forceinline__ void corr_cell(const float q[8], const float c[8], const float xm[8], const float ym[8],
                                           const float zm[8], const float xp[8], const float yp[8], const float zp[8],
                                           const Params& P, float out[8]) {
@@ -122,11 +123,18 @@ __device__ __forceinline__ void corr_cell(const float q[8], const float c[8], co
     flux_loc<DIR_X>(c, sc, fc);
     flux_loc<DIR_Y>(c, sc, gc);
     flux_loc<DIR_Z>(c, sc, hc);
-    flux_loc<DIR_X>(xm, make_prim(xm), fi);
     // G'(Qint(i,j-1,k)) is what lane-1 has just computed as its own gc (same inputs, same function, same bits): one
     // shuffle per component instead of re-deriving the neighbour's primitives and flux.  Lane 0 never writes output.
+    // With lanes along i (remainder-strip kernel) the same holds for F'(Qint(i-1,j,k)) instead.
+    if (LANES_I) {
+        flux_loc<DIR_Y>(ym, make_prim(ym), gj);
 #pragma unroll
-    for (int v = 0; v < 8; ++v) gj[v] = v == BY ? 0.0f : __shfl_up_sync(0xffffffffu, gc[v], 1);
+        for (int v = 0; v < 8; ++v) fi[v] = v == BX ? 0.0f : __shfl_up_sync(0xffffffffu, fc[v], 1);
+    } else {
+        flux_loc<DIR_X>(xm, make_prim(xm), fi);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) gj[v] = v == BY ? 0.0f : __shfl_up_sync(0xffffffffu, gc[v], 1);
+    }
     {   // k-1 point with the reference's mixed neighbours: Bsq from (Bx(i-1), By(j-1), Bz(k-1)) (B-4), Bdotu with
         // rhovy(j-1) (B-5); KE and the velocities from the k-1 state itself
         Prim sk;
@@ -519,6 +527,145 @@ __global__ void __launch_bounds__(TI * 32, 1) k_fused_step_tma(const FusedArgs A
 #undef IMHD_MARCH
 }
 
+// -----------------------------------------------------------------------------------------------
+// Remainder strip.  The tiles of the hot kernel produce 30 (path A: 31) output columns each; when Ny leaves a
+// remainder of a few columns (304 -> 10 x 30 + 2) a whole extra tile column -- 9 % of the launch at 304 -- would
+// compute them with 2 of 32 lanes.  This kernel takes the last columns instead, TRANSPOSED: lanes run along i and
+// the R = blockDim.y thread rows along j (one row of predictor-only ring, the output columns, and for path B the
+// wall column), so a block is 32 x R cells and four such blocks share an SM.  The Q planes come through a rotating
+// three-plane staging tile [v][i][8 columns] filled by cp.async with a loader mapping in which 8 consecutive
+// threads read the 8 consecutive columns of one i-row (one 32-byte sector).  Same device functions, same inputs
+// -> the same bits as any other variant (tests).
+// -----------------------------------------------------------------------------------------------
+constexpr int kStripCols = 8;   // staging-tile columns: the compute rows and one column either side
+constexpr int kStripRows = 6;   // at most this many compute rows
+
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+template <int PATH>
+__global__ void __maxnreg__(168) k_fused_strip(const FusedArgs A) {
+    constexpr int O = Ring<PATH>::O;
+    constexpr int WL = 32 - 2 * O;
+    constexpr int PITCH = kStripCols + 1;          // tile rows padded against bank conflicts
+    constexpr int NB = 8 * 32 * PITCH;
+    extern __shared__ float strip_smem[];
+    float* sQi = strip_smem;                         // exchange of Qint(k): [2][v][tj][lane]
+    float* sN = strip_smem + 2 * 8 * kStripRows * 32;  // Q planes k+1 (neighbour reads), k+2 (own read), k+3, k+4 (in flight)
+
+    const Params& P = A.P;
+    const int lane = threadIdx.x, tj = threadIdx.y, R = blockDim.y;
+    const int bi = blockIdx.x;
+    const int i = bi * WL + 1 - O + lane, j = A.jstrip + 1 + tj;   // tile column tj+1
+    const bool in_dom = i >= 0 && i < P.Nx && j < P.Ny;
+    const int ic = min(max(i, 0), P.Nx - 1), jc = min(j, P.Ny - 1);
+    const long long lcol = (long long)ic * P.Ny + jc;
+    const bool top = (i == 0), bottom = (i == P.Nx - 1), right = (j == P.Ny - 1);
+    const bool interior_ij = in_dom && !top && !bottom && !right;   // j > 0 always: the strip sits at the far wall
+    const bool upd = PATH == IMHD_PATH_A ? (in_dom && !top) : interior_ij;
+    const int oi_lo = bi == 0 ? 0 : 1 + bi * WL, oi_hi = bi == A.ntile_i - 1 ? P.Nx : 1 + (bi + 1) * WL;
+    const bool owner = in_dom && i >= oi_lo && i < oi_hi && tj >= 1;  // row 0 is the predictor-only ring
+    const int so = tj * 32 + lane, sjm = max(tj - 1, 0) * 32 + lane, sjp = min(tj + 1, R - 1) * 32 + lane;
+    const int st_own = lane * PITCH + tj + 1;
+
+    const int ka = A.kfrom + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kto);
+    const bool first = ka == A.ka0;
+    const int ks = first ? ka - 1 : ka - 2;
+    auto plane_off = [&](int k) -> long long {
+        const int kc = min(max(k, A.kmin), A.kmax);
+        return (long long)(kc - A.kbase) * P.plane;
+    };
+    const int nthr = 32 * R, t = tj * 32 + lane;
+    auto fill = [&](int k, float* buf) {  // asynchronous: plane k of the strip into a staging buffer
+        const float* src = A.Qin + plane_off(k);
+        for (int e = t; e < 32 * kStripCols; e += nthr) {
+            const int li = e >> 3, lj = e & 7;
+            const long long col = (long long)min(max(bi * WL + 1 - O + li, 0), P.Nx - 1) * P.Ny + min(A.jstrip + lj, P.Ny - 1);
+#pragma unroll
+            for (int v = 0; v < 8; ++v) cp_async4(buf + v * 32 * PITCH + li * PITCH + lj, src + v * A.vs + col);
+        }
+    };
+
+    float q0[8], q1[8], h1[8], qim[8], qic[8];
+    fill(ks + 1, sN);
+    fill(ks + 2, sN + NB);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    fill(ks + 3, sN + 2 * NB);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    ldg8(A.Qin + plane_off(ks) + lcol, 0, A.vs, q0);
+    ldg8(A.Qin + plane_off(ks + 1) + lcol, 0, A.vs, q1);
+    hflux(q1, h1);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) { qim[v] = 1.0f; qic[v] = 1.0f; }
+    if (first) ldg8(A.qlo, lcol, P.plane, qic);
+
+    float* outp = A.Qout + (long long)(ka - A.kbase) * P.plane + lcol;
+    int b1 = 0;  // staging buffer of plane k+1; k+2, k+3 follow, k+4 goes to b1+3 (mod 4)
+    for (int k = ks; k < kb; ++k) {
+        const int buf = (k - ks) & 1;
+        const int b2 = (b1 + 1) & 3, b4 = (b1 + 3) & 3;
+        float qn[8], hn[8], qip[8];
+        const float* bQ = sN + b1 * NB;
+        const float* bN = sN + b2 * NB;
+        float* bQi = sQi + buf * 8 * kStripRows * 32;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) bQi[v * kStripRows * 32 + so] = qic[v];
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // plane k+2 has landed; k+3 may still be in flight
+        __syncthreads();
+        if (k + 2 < kb) fill(k + 4, sN + b4 * NB);  // two planes ahead; b4 held plane k, which nobody reads any more
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        b1 = b2;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) qn[v] = bN[v * 32 * PITCH + st_own];
+        hflux(qn, hn);
+        if (k + 1 == A.hi_plane) {
+            ldg8(A.qhi, lcol, P.plane, qip);
+        } else {
+            float xp[8], yp[8], xm[8], ym[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                xp[v] = __shfl_down_sync(0xffffffffu, q1[v], 1);
+                yp[v] = bQ[v * 32 * PITCH + st_own + 1];
+            }
+            if (PATH == IMHD_PATH_B) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    xm[v] = __shfl_up_sync(0xffffffffu, q1[v], 1);
+                    ym[v] = bQ[v * 32 * PITCH + st_own - 1];
+                }
+            }
+            qint_cell<PATH>(q1, xp, yp, h1, hn, xm, ym, q0, qn, bottom, right, false, interior_ij, P, qip);
+        }
+        if (k >= ka) {
+            float out[8], xm[8], ym[8], xp[8], yp[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                xm[v] = __shfl_up_sync(0xffffffffu, qic[v], 1);
+                ym[v] = bQi[v * kStripRows * 32 + sjm];
+            }
+            if (PATH == IMHD_PATH_B) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    xp[v] = __shfl_down_sync(0xffffffffu, qic[v], 1);
+                    yp[v] = bQi[v * kStripRows * 32 + sjp];
+                }
+            }
+            corr_cell<PATH, true>(q0, qic, xm, ym, qim, xp, yp, qip, P, out);
+            if (owner) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) outp[v * A.vs] = upd ? out[v] : q0[v];
+            }
+            outp += P.plane;
+        }
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            q0[v] = q1[v]; q1[v] = qn[v]; h1[v] = hn[v];
+            qim[v] = qic[v]; qic[v] = qip[v];
+        }
+    }
+}
+
 // Predictor plane k (global index, k <= Nz-2) into an (8,Nx,Ny) buffer: same device function, same
 // values as the fused kernel computes on chip.
 template <int PATH>
@@ -651,7 +798,7 @@ static int fill_args(FusedArgs& A, const float* Qin, float* Qout, const float* q
     A.qlo = qlo; A.qhi = qhi; A.qwrap = qwrap;
     A.hi_plane = min(A.k1, s->Nz - 1);
     A.corner_e = s->corner_e;
-    A.chunk = 0; A.ntile_i = A.ntile_j = 0;
+    A.chunk = 0; A.ntile_i = A.ntile_j = 0; A.jstrip = 0;
     return 0;
 }
 
@@ -697,8 +844,8 @@ static PFN_cuTensorMapEncodeTiled get_encode() {
     return fn;
 }
 
-static int g_force_ldg = 0;
-extern "C" void imhd_set_kernel_variant(int force_plain_loads) { g_force_ldg = force_plain_loads; }
+static int g_force_ldg = 0, g_no_strip = 0;
+extern "C" void imhd_set_kernel_variant(int flags) { g_force_ldg = flags & 1; g_no_strip = (flags >> 1) & 1; }
 
 // 4-D view (j, i, plane, variable) of a state array for the tile loads of the TMA kernel.
 static bool make_tile_map(CUtensorMap* map, const FusedArgs& A, int nplanes, int tile_rows) {
@@ -727,14 +874,14 @@ static int ensure_smem(K kernel, size_t bytes, unsigned long long& done_mask) {
     return 0;
 }
 
-static int pick_chunk(FusedArgs& A, int nz) {
+static int pick_chunk(FusedArgs& A, int nz, long long tiles = 0) {
     // z-chunks: one block per SM is resident (register-limited), so the launch runs in waves of `sms` blocks.  Pick the
     // chunk count that minimises  waves x (chunk length + warm-up)  -- i.e. fill the last wave -- with chunks long
     // enough to amortise the two warm-up planes (each costs about half a plane).
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long tiles = (long long)A.ntile_i * A.ntile_j;
+    if (tiles <= 0) tiles = (long long)A.ntile_i * A.ntile_j;
     int best_n = 1;
     double best = 1e300;
     const int nmax = nz / 12 > 1 ? nz / 12 : 1;
@@ -764,11 +911,41 @@ static int launch_fused(FusedArgs& A, int nplanes_array, cudaStream_t st) {
         using G = TmaGeo<PATH, TI>;
         A.ntile_i = (ni + G::WI - 1) / G::WI;
         A.ntile_j = (nj + G::WJ - 1) / G::WJ;
-        const int nchunk = pick_chunk(A, nz);
+        // a remainder of a few columns goes to the transposed strip kernel instead of a whole extra tile column
+        constexpr int O = Ring<PATH>::O;
+        const int rem = nj % G::WJ;
+        const int strip_rows = PATH == IMHD_PATH_A ? 1 + rem : 1 + rem + 1;  // predictor-only ring row, outputs (, wall column)
+        const bool strip = !g_no_strip && rem > 0 && strip_rows <= kStripRows && nj / G::WJ >= 2;
+        int grid_j = A.ntile_j;
+        if (strip) {
+            grid_j = nj / G::WJ;
+            A.ntile_j = grid_j + 1;  // no hot-kernel tile is the last one: none widens its window to the domain edge
+        }
+        const int nchunk = pick_chunk(A, nz, (long long)A.ntile_i * grid_j);
         static unsigned long long done = 0;
         if (int e = ensure_smem(k_fused_step_tma<PATH, TI>, G::SMEM, done)) return e;
-        k_fused_step_tma<PATH, TI><<<dim3(A.ntile_j, A.ntile_i, nchunk), dim3(32, TI), G::SMEM, st>>>(A, tmap);
+        k_fused_step_tma<PATH, TI><<<dim3(grid_j, A.ntile_i, nchunk), dim3(32, TI), G::SMEM, st>>>(A, tmap);
         IMHD_LAUNCH_CHECK(1);
+        if (strip) {
+            FusedArgs S = A;
+            constexpr int WL = 32 - 2 * O;
+            S.ntile_i = (ni + WL - 1) / WL;
+            S.jstrip = grid_j * G::WJ - 1;          // tile column 0; the ring row sits at jstrip + 1 = the last hot-kernel output
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            int n = (3 * sms + S.ntile_i - 1) / S.ntile_i;      // a few small blocks per SM
+            n = n > nz / 8 ? nz / 8 : n;
+            n = n < 1 ? 1 : n;
+            S.chunk = (nz + n - 1) / n;
+            if (g_chunk_override > 0) S.chunk = g_chunk_override;
+            S.chunk = S.chunk < 2 ? 2 : (S.chunk > nz ? nz : S.chunk);
+            constexpr size_t strip_smem = (2 * 8 * kStripRows * 32 + 4 * 8 * 32 * (kStripCols + 1)) * sizeof(float);
+            static unsigned long long sdone = 0;
+            if (int e = ensure_smem(k_fused_strip<PATH>, strip_smem, sdone)) return e;
+            k_fused_strip<PATH><<<dim3(S.ntile_i, 1, (nz + S.chunk - 1) / S.chunk), dim3(32, strip_rows), strip_smem, st>>>(S);
+            IMHD_LAUNCH_CHECK(1);
+        }
         return 0;
     }
     constexpr int O = Ring<PATH>::O;

@@ -156,10 +156,10 @@ int imhd_stability_scan(const float* Q, const imhd_slab* s, imhd_stability* host
  * x-thread of the reference launch re-applies it).  Scalar host helper, identity when e == 0. */
 float imhd_wall_energy_fixed_point(float e, int max_iter);
 
-/* Test hooks: force the z-chunk length of the fused kernel (0 = automatic); force the plain-load
- * variant of the fused kernel instead of the TMA one (both give the same bits). */
+/* Test hooks: force the z-chunk length of the fused kernel (0 = automatic); kernel-variant flags: bit 0 forces the
+ * plain-load variant instead of the TMA one, bit 1 disables the remainder-strip kernel (all give the same bits). */
 void imhd_set_chunk(int planes);
-void imhd_set_kernel_variant(int force_plain_loads);
+void imhd_set_kernel_variant(int flags);
 
 /* Predictor plane Qint(.,.,k) for one owned global plane k into an (8,Nx,Ny) device buffer
  * (the data a neighbouring slab needs as qint_lo / qint_hi). */

@@ -298,6 +298,29 @@ def test_tma_and_plain_load_variants_give_the_same_bits(imhd, torch, O, oracle_m
         assert bits_equal(a, b), path
 
 
+@pytest.mark.parametrize("dims", [(40, 64, 21), (36, 96, 30), (64, 64, 40)])
+def test_remainder_strip_kernel_gives_the_same_bits(imhd, torch, O, oracle_mod, dims):
+    """When Ny leaves a few columns beyond the 30-wide (path A: 31-wide) tiles, a transposed strip kernel computes
+    them instead of a whole extra tile column (304 = 10 x 30 + 2 + walls).  Same bits with and without it, under any
+    chunking, and against the plain-load variant (which never uses the strip)."""
+    om = oracle_mod
+    lib = imhd._lib.load()
+    g, d, Q0 = make_case(O, om, *dims, ic="bennett")
+    Q0 = Q0 + 0.01 * random_state(*dims, seed=3)   # break the symmetry of the analytic IC
+    for path, D in paths(om):
+        a = run_fused(imhd, Q0, path, D, DT, d, 5)
+        try:
+            lib.imhd_set_kernel_variant(2)          # strip off: the hot kernel's extra tile column does the work
+            b = run_fused(imhd, Q0, path, D, DT, d, 5)
+            lib.imhd_set_kernel_variant(1)          # plain loads
+            c = run_fused(imhd, Q0, path, D, DT, d, 5)
+        finally:
+            lib.imhd_set_kernel_variant(0)
+        assert bits_equal(a, b) and bits_equal(a, c), path
+        for chunk in (2, 7):
+            assert bits_equal(run_fused(imhd, Q0, path, D, DT, d, 5, chunk=chunk), a), (path, chunk)
+
+
 def test_fused_matches_granular_on_device(imhd, torch, O, oracle_mod):
     """Two independent CUDA implementations of the same step agree to rounding."""
     om = oracle_mod
