@@ -844,8 +844,10 @@ static PFN_cuTensorMapEncodeTiled get_encode() {
     return fn;
 }
 
-static int g_force_ldg = 0, g_no_strip = 0;
-extern "C" void imhd_set_kernel_variant(int flags) { g_force_ldg = flags & 1; g_no_strip = (flags >> 1) & 1; }
+static int g_force_ldg = 0, g_no_strip = 0, g_force_strip = 0;
+extern "C" void imhd_set_kernel_variant(int flags) {
+    g_force_ldg = flags & 1; g_no_strip = (flags >> 1) & 1; g_force_strip = (flags >> 2) & 1;
+}
 
 // 4-D view (j, i, plane, variable) of a state array for the tile loads of the TMA kernel.
 static bool make_tile_map(CUtensorMap* map, const FusedArgs& A, int nplanes, int tile_rows) {
@@ -915,7 +917,9 @@ static int launch_fused(FusedArgs& A, int nplanes_array, cudaStream_t st) {
         constexpr int O = Ring<PATH>::O;
         const int rem = nj % G::WJ;
         const int strip_rows = PATH == IMHD_PATH_A ? 1 + rem : 1 + rem + 1;  // predictor-only ring row, outputs (, wall column)
-        const bool strip = !g_no_strip && rem > 0 && strip_rows <= kStripRows && nj / G::WJ >= 2;
+        // (not for short plane ranges such as the slab-end launches of the multi-GPU loop: there the strip's fixed
+        // latency costs more than the extra tile column; the test hook bit 2 forces it on for any length)
+        const bool strip = !g_no_strip && rem > 0 && strip_rows <= kStripRows && nj / G::WJ >= 2 && (nz >= 64 || g_force_strip);
         int grid_j = A.ntile_j;
         if (strip) {
             grid_j = nj / G::WJ;

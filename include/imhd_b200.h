@@ -157,7 +157,8 @@ int imhd_stability_scan(const float* Q, const imhd_slab* s, imhd_stability* host
 float imhd_wall_energy_fixed_point(float e, int max_iter);
 
 /* Test hooks: force the z-chunk length of the fused kernel (0 = automatic); kernel-variant flags: bit 0 forces the
- * plain-load variant instead of the TMA one, bit 1 disables the remainder-strip kernel (all give the same bits). */
+ * plain-load variant instead of the TMA one, bit 1 disables the remainder-strip kernel, bit 2 uses it even for
+ * plane ranges shorter than 64 (all give the same bits). */
 void imhd_set_chunk(int planes);
 void imhd_set_kernel_variant(int flags);
 

@@ -253,13 +253,15 @@ def test_fused_cell_sets_bit_exact(imhd, torch, O, oracle_mod):
             assert (om.normalised_linf(Q[:, :1], qo[:, :1]) <= 1e-6).all()
 
 
-def test_plane_range_launches_compose(imhd, torch, O, oracle_mod):
+@pytest.mark.parametrize("dims,variant", [((40, 36, 29), 0), ((36, 64, 29), 4)])  # 4: remainder-strip kernel forced on
+def test_plane_range_launches_compose(imhd, torch, O, oracle_mod, dims, variant):
     """imhd_step_fused_planes over any split of the owned planes == one imhd_step_fused call, bit for bit."""
     om, ops = oracle_mod, imhd.ops
-    dims = (40, 36, 29)
     Nx, Ny, Nz = dims
     g, d, Q0 = make_case(O, om, *dims, ic="bennett")
+    lib = imhd._lib.load()
     for path, D in paths(om):
+        lib.imhd_set_kernel_variant(variant)
         Qin = dev(torch, Q0)
         ref, out = torch.empty_like(Qin), torch.full_like(Qin, float("nan"))
         s = ops.make_slab(Nx, Ny, Nz, path, D, DT, *d)
@@ -268,6 +270,7 @@ def test_plane_range_launches_compose(imhd, torch, O, oracle_mod):
         ops.step_fused(Qin, ref, q0, q0, qw, s)
         for a, b in ((20, Nz), (0, 5), (5, 6), (6, 20)):   # out of order on purpose
             ops.step_fused_planes(Qin, out, q0, q0, qw, s, a, b)
+        lib.imhd_set_kernel_variant(0)
         assert bits_equal(out.cpu().numpy(), ref.cpu().numpy()), path
 
 
@@ -308,8 +311,11 @@ def test_remainder_strip_kernel_gives_the_same_bits(imhd, torch, O, oracle_mod, 
     g, d, Q0 = make_case(O, om, *dims, ic="bennett")
     Q0 = Q0 + 0.01 * random_state(*dims, seed=3)   # break the symmetry of the analytic IC
     for path, D in paths(om):
-        a = run_fused(imhd, Q0, path, D, DT, d, 5)
         try:
+            lib.imhd_set_kernel_variant(4)          # strip on (by default only plane ranges >= 64 use it)
+            a = run_fused(imhd, Q0, path, D, DT, d, 5)
+            for chunk in (2, 7):
+                assert bits_equal(run_fused(imhd, Q0, path, D, DT, d, 5, chunk=chunk), a), (path, chunk)
             lib.imhd_set_kernel_variant(2)          # strip off: the hot kernel's extra tile column does the work
             b = run_fused(imhd, Q0, path, D, DT, d, 5)
             lib.imhd_set_kernel_variant(1)          # plain loads
@@ -317,8 +323,6 @@ def test_remainder_strip_kernel_gives_the_same_bits(imhd, torch, O, oracle_mod, 
         finally:
             lib.imhd_set_kernel_variant(0)
         assert bits_equal(a, b) and bits_equal(a, c), path
-        for chunk in (2, 7):
-            assert bits_equal(run_fused(imhd, Q0, path, D, DT, d, 5, chunk=chunk), a), (path, chunk)
 
 
 def test_fused_matches_granular_on_device(imhd, torch, O, oracle_mod):
