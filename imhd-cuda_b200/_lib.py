@@ -112,6 +112,8 @@ def load() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError here == header/library mismatch
             fn.restype, fn.argtypes = res, args
+        if os.environ.get("IMHD_KERNEL_VARIANT"):  # kernel experiments: see imhd_set_kernel_variant in the header
+            lib.imhd_set_kernel_variant(int(os.environ["IMHD_KERNEL_VARIANT"]))
         _lib = lib
     return _lib
 
