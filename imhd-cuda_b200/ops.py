@@ -285,6 +285,20 @@ class Context:
         check(self.L.imhd_ctx_get_grids(self.h, *(a.ctypes.data_as(C.c_void_p) for a in (x, y, z))))
         return x, y, z
 
+    # ---- output (src/on-device/utils/phdf5_write_all.cpp, hdf5_write_grid.cpp; asynchronous, see imhd_ctx_write_frame) ----
+    def write_frame(self, directory: str, frame: int):
+        """Queue the current state as <directory>/fluidvars_<frame>.h5; returns at once."""
+        d = directory if directory.endswith("/") else directory + "/"
+        check(self.L.imhd_ctx_write_frame(self.h, d.encode(), frame))
+
+    def write_grid(self, directory: str):
+        d = directory if directory.endswith("/") else directory + "/"
+        check(self.L.imhd_ctx_write_grid(self.h, d.encode()))
+
+    def flush_output(self):
+        """Wait until every queued frame is on disk; raises if a write failed."""
+        check(self.L.imhd_ctx_flush_output(self.h))
+
     def run_host(self, Q_in: np.ndarray, Q_out: np.ndarray, path, D, dt, dx, dy, dz, nsteps):
         check(self.L.imhd_run_host(self.h, Q_in.ctypes.data_as(C.c_void_p), Q_out.ctypes.data_as(C.c_void_p), path, D,
                                    dt, dx, dy, dz, nsteps))

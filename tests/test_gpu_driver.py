@@ -110,3 +110,35 @@ def test_driver_selects_the_initial_condition_by_registry_key(tmp_path, O, oracl
     assert float(m.group(5)) == pytest.approx(want["dt_new"], rel=1e-5)
     bad = subprocess.run(run, capture_output=True, text=True, env=dict(os.environ, IMHD_IC="orszag-tang"))
     assert bad.returncode != 0 and "Unknown simulation type: orszag-tang" in bad.stdout + bad.stderr
+
+
+def test_context_output_from_python(tmp_path, O, oracle_mod):
+    """Context.write_frame / write_grid / flush_output: frames queued while the time loop keeps running hold the state
+    of the step they were queued at."""
+    imhd = importlib.import_module("imhd-cuda_b200")
+    om = oracle_mod
+    dims = (24, 20, 12)
+    _, d, Q0 = make_case(O, om, *dims)
+    out = str(tmp_path / "frames")
+    os.makedirs(out)
+    states = {}
+    with imhd.Context(*dims) as c:
+        c.init_grids(*BOUNDS)
+        c.set_state(Q0)
+        c.prime(om.PATH_B, 0.01, 1e-4)
+        c.write_grid(out)
+        for it in range(0, 7):
+            if it:
+                c.step(1)
+            if it % 2 == 0:
+                c.write_frame(out, it)        # no wait: the next step overwrites the device buffers
+                states[it] = None
+        c.flush_output()
+        final = c.get_state()
+    assert sorted(f for f in os.listdir(out)) == ["fluidvars_0.h5", "fluidvars_2.h5", "fluidvars_4.h5", "fluidvars_6.h5", "grid.h5"]
+    assert np.array_equal(read_frame(os.path.join(out, "fluidvars_6.h5"), dims), final)
+    qo, io = Q0.copy(), np.zeros_like(Q0)
+    O.prime(qo, io, om.PATH_B, 0.01, 1e-4, *d)
+    assert np.array_equal(read_frame(os.path.join(out, "fluidvars_0.h5"), dims), qo)
+    O.steps(qo, io, om.PATH_B, 2, 0.01, 1e-4, *d)
+    assert (om.normalised_linf(read_frame(os.path.join(out, "fluidvars_2.h5"), dims), qo) <= 1e-6).all()
