@@ -307,7 +307,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.workload,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "finite": finite,
-            "roofline": {"bound": "hbm", "kernel": "k_fused_step_tma<PATH_B,16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_fused_step_tma<PATH_B,16> (+ k_fused_strip<PATH_B> for the columns beyond the last full tile; timed together)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_cell_update": BYTES_PER_CELL_UPDATE,
                          "cell_updates_per_launch": cells_launch, "avg_launch_ms": fused_ms,
                          "traffic": ncu_traffic_per_launch(cells_launch)},
