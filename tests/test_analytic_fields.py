@@ -107,3 +107,38 @@ def test_pressure_gradient_accelerates_down_the_gradient(O, oracle_mod):
     assert np.allclose(interior(Qi)[1], -DT * (GAMMA - 1) * slope, rtol=0, atol=2e-7)
     assert not interior(Qi)[2].any() and not interior(Qi)[3].any()
     assert np.array_equal(interior(Qi)[0], interior(Q)[0])
+
+
+def test_entropy_wave_converges_at_second_order(O, oracle_mod):
+    """"Kernels vs problem size" (tests/README.md:6-9): a density wave carried along the periodic z axis by a uniform
+    flow (constant pressure, no field) is an exact solution rho(z - u t) of the reference's equations too (its
+    kinetic-energy convention, B-1, is used consistently).  Lax-Wendroff must converge on it at second order: halving
+    dz at fixed CFL number divides the error by ~4.  A flow ALONG the rigid walls is unstable in the reference's wall
+    treatment (the wall cells blow up within ten steps) and its one-sided periodic seam (plane 0 is a copy of plane
+    Nz-1, kernels_fluidbcs.cu:498-510) sheds plane-to-plane noise that grows with the step count, so the error is
+    measured away from both: a cross-section wider than the walls' reach in these few steps, and only the planes far
+    from the seam (measured ratio 33 -> 65 planes: 4.08)."""
+    om = oracle_mod
+    u0, p0, eps, Lz, T = 1.0, 1.0, 0.05, 1.0, 0.1
+    errs = []
+    for nz in (33, 65):
+        nsteps = 5 * (nz - 1) // 16             # dt = T / nsteps: (u + c_s) dt/dz = 0.73 at both resolutions
+        Nx = Ny = 2 * nsteps + 6
+        dz = Lz / (nz - 1)                      # period of the reference's z axis: Nz - 1 intervals (plane Nz-1 == plane 0)
+        dx = dy = 2.0
+        z = dz * np.arange(nz)
+        rho = 1.0 + eps * np.sin(2 * np.pi * z / Lz)
+        Q = np.zeros((8, nz, Nx, Ny), np.float32)
+        Q[0] = rho.reshape(-1, 1, 1)
+        Q[3] = (rho * u0).reshape(-1, 1, 1)
+        Q[7] = (p0 / (GAMMA - 1) + rho * u0 * u0).reshape(-1, 1, 1)   # e = p/(gamma-1) + KE with KE = rho v^2 (B-1)
+        dt = T / nsteps
+        Qi = np.zeros_like(Q)
+        O.prime(Q, Qi, om.PATH_A, 0.0, dt, dx, dy, dz)
+        O.steps(Q, Qi, om.PATH_A, nsteps, 0.0, dt, dx, dy, dz)
+        exact = 1.0 + eps * np.sin(2 * np.pi * (z - u0 * T) / Lz)
+        col = Q[0, :, Nx // 2, Ny // 2].astype(np.float64)
+        w = slice(nsteps + 2, nz - nsteps - 2)
+        errs.append(np.sqrt(np.mean((col[w] - exact[w]) ** 2)))
+    assert errs[0] < 0.2 * eps                  # the coarse run already tracks the wave
+    assert 3.0 < errs[0] / errs[1] < 5.5, errs  # second order
