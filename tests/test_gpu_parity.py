@@ -442,3 +442,33 @@ def test_production_size_properties(imhd, torch, O, oracle_mod):
     mid = Q[:, 2 * n + 2]
     for k in (2 * n + 3, Nz // 2, Nz - 2 * n - 3):
         assert bits_equal(Q[:, k], mid), f"plane {k} lost z-invariance"
+
+
+def test_fused_path_converges_at_second_order(imhd, torch, O, oracle_mod):
+    """Physics-level check of the product path through the C ABI: the advected density wave of
+    tests/test_analytic_fields.py (an exact solution) converges at second order with the fused kernels too."""
+    om = oracle_mod
+    gamma = 5.0 / 3.0
+    u0, p0, eps, Lz, T = 1.0, 1.0, 0.05, 1.0, 0.1
+    errs = []
+    for nz in (33, 65):
+        nsteps = 5 * (nz - 1) // 16
+        Nx = Ny = 2 * nsteps + 6
+        dz, dx, dy = Lz / (nz - 1), 2.0, 2.0
+        z = dz * np.arange(nz)
+        rho = 1.0 + eps * np.sin(2 * np.pi * z / Lz)
+        Q = np.zeros((8, nz, Nx, Ny), np.float32)
+        Q[0] = rho.reshape(-1, 1, 1)
+        Q[3] = (rho * u0).reshape(-1, 1, 1)
+        Q[7] = (p0 / (gamma - 1) + rho * u0 * u0).reshape(-1, 1, 1)
+        dt = T / nsteps
+        with imhd.Context(Nx, Ny, nz) as c:
+            c.set_state(Q)
+            c.set_spacing(dx, dy, dz)
+            c.prime(om.PATH_A, 0.0, dt)
+            c.step(nsteps)
+            col = c.get_state()[0, :, Nx // 2, Ny // 2].astype(np.float64)
+        exact = 1.0 + eps * np.sin(2 * np.pi * (z - u0 * T) / Lz)
+        w = slice(nsteps + 2, nz - nsteps - 2)
+        errs.append(np.sqrt(np.mean((col[w] - exact[w]) ** 2)))
+    assert errs[0] < 0.2 * eps and 3.0 < errs[0] / errs[1] < 5.5, errs
