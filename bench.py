@@ -33,11 +33,18 @@ J0, D, DT = 1.0, 0.01, 1e-4
 BYTES_PER_CELL_UPDATE = 64  # 8 fp32 read + 8 fp32 written
 
 
-def spacing(nz_global):
+def spacing(nz_per_gpu):
+    """Grid spacing of the workload.  Weak scaling EXTENDS the domain in z (z_max = z_min + (Nz-1) dz with dz the
+    N = 1 spacing) instead of refining it: squeezing 592 N planes into the same box would push the explicit
+    diffusion past its stability limit dt D (2/dx^2 + 2/dy^2 + 2/dz^2) < 1/2 (lib/on-device/diffusion.cu:8-19)."""
     import numpy as np
 
     f = lambda lo, hi, n: float(np.float32((np.float32(hi) - np.float32(lo)) / np.float32(n - 1)))  # noqa: E731
-    return f(BOUNDS[0], BOUNDS[1], NX), f(BOUNDS[2], BOUNDS[3], NY), f(BOUNDS[4], BOUNDS[5], nz_global)
+    return f(BOUNDS[0], BOUNDS[1], NX), f(BOUNDS[2], BOUNDS[3], NY), f(BOUNDS[4], BOUNDS[5], nz_per_gpu)
+
+
+def diffusion_number(dx, dy, dz):
+    return DT * D * (2.0 / dx**2 + 2.0 / dy**2 + 2.0 / dz**2)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -142,10 +149,13 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n):
+def workload_config(n, weak=True):
+    dx, dy, dz = spacing(NZ_PER_GPU if weak else NZ_PER_GPU * n)
     return {"workload": f"Bennett screw pinch {NX}x{NY}x{NZ_PER_GPU * n} fp32, numerical diffusion on (D={D}), dt={DT}, "
                         f"reference pipeline src/on-device/main.cu (path B)",
             "grid": [NX, NY, NZ_PER_GPU * n], "decomposition": f"z-slabs x{n}" if n > 1 else "single GPU",
+            "spacing": [dx, dy, dz], "z_extent": dz * (NZ_PER_GPU * n - 1),
+            "diffusion_number": diffusion_number(dx, dy, dz),  # dt D (2/dx^2+2/dy^2+2/dz^2), explicit limit 1/2
             "l2": f"inputs ({8 * 4 * NX * NY * NZ_PER_GPU / 1e9:.2f} GB per array per GPU) larger than L2, no flush needed"}
 
 
@@ -199,7 +209,7 @@ def main():
         NX, NY = STRONG[0], STRONG[1]
         NZ_PER_GPU = STRONG[2] // world
     nz_global = NZ_PER_GPU * world
-    dx, dy, dz = spacing(nz_global)
+    dx, dy, dz = spacing(NZ_PER_GPU) if args.workload == "weak" else spacing(nz_global)
     solver = slabmod.SlabSolver(NX, NY, nz_global, pkg.PATH_B, D, DT, dx, dy, dz, comm=comm, corner_e=0.0)
     L = solver.layout
     cells_local = NX * NY * L.nzl
@@ -305,7 +315,7 @@ def main():
         line = {
             "metric": "cell_updates_per_sec", "value": value, "unit": "GLUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.workload,
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, args.workload == "weak"), "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "finite": finite,
             "roofline": {"bound": "hbm", "kernel": "k_fused_step_tma<PATH_B,16> (+ k_fused_strip<PATH_B> for the columns beyond the last full tile; timed together)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_cell_update": BYTES_PER_CELL_UPDATE,
@@ -318,6 +328,8 @@ def main():
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    if not finite:
+        raise SystemExit("bench.py: the state is not finite after the timed steps -- the number above is not a measurement")
 
 
 if __name__ == "__main__":
