@@ -39,6 +39,8 @@ struct FusedArgs {
     const float* Qin;   // variable 0, array plane 0
     float* Qout;
     long long vs;       // variable stride of Qin/Qout in floats
+    unsigned vs32;      // the same, unsigned 32-bit: 8 * vs * 4 B < 180 GB keeps vs below 2^32, so an output address is ONE
+                        // 32x32->64-bit multiply-add on the 64-bit plane pointer
     int kbase;          // global plane index held by array plane 0
     int kmin, kmax;     // global planes that may be READ from Qin: [kmin, kmax]
     int k0, k1;         // owned (written) global planes [k0, k1)
@@ -68,32 +70,30 @@ __device__ __forceinline__ void ldg8(const float* __restrict__ A, long long off,
 __device__ __forceinline__ void hflux(const float U[8], float h[8]) { flux_idx<DIR_Z>(U, make_prim(U), h); }
 
 // -----------------------------------------------------------------------------------------------
-// Predictor at one cell from raw states (fast recipe).  c = Q(i,j,k), xp = Q(i+1,j,k),
-// yp = Q(i,j+1,k), hc = H(Q(i,j,k)), hp = H(Q(i,j,k+1)); xm, ym, zm, zp only when `lap`.
+// Predictor at one cell (fast recipe), from fluxes that are already evaluated -- so a caller that
+// holds the neighbour's flux (register-tiled rows, shuffles) does not derive it twice:
+//   c = Q(i,j,k);  fc, fxp = F(Q) at the cell and at i+1;  gc, gyp = G(Q) at the cell and at j+1;
+//   hc, hp = H(Q) at the cell and at k+1;  xm..zp = the six neighbours of c (only when `lap`).
 // Cell classes and typos: kernels_od_intvar.cu:1160-1253, kernels_intvarbcs.cu:560-1110 (B-15).
 // -----------------------------------------------------------------------------------------------
 template <int PATH>
-__device__ __forceinline__ void qint_cell(const float c[8], const float xp[8], const float yp[8], const float hc[8],
-                                          const float hp[8], const float xm[8], const float ym[8], const float zm[8],
-                                          const float zp[8], bool bottom, bool right, bool front, bool lap,
-                                          const Params& P, float out[8]) {
-    const Prim s = make_prim(c);
-    float f[8], g[8], t[8], dF[8], dG[8], dH[8];
-    flux_idx<DIR_X>(c, s, f);
-    flux_idx<DIR_Y>(c, s, g);
-    flux_idx<DIR_X>(xp, make_prim(xp), t);
+__device__ __forceinline__ void qint_combine(const float c[8], const float fc[8], const float fxp[8], const float gc[8],
+                                             const float gyp[8], const float hc[8], const float hp[8], const float xm[8],
+                                             const float xp[8], const float ym[8], const float yp[8], const float zm[8],
+                                             const float zp[8], bool bottom, bool right, bool front, bool lap,
+                                             const Params& P, float out[8]) {
+    float dF[8], dG[8], dH[8];
 #pragma unroll
-    for (int v = 0; v < 8; ++v) dF[v] = bottom ? -f[v] : t[v] - f[v];
-    flux_idx<DIR_Y>(yp, make_prim(yp), t);
-#pragma unroll
-    for (int v = 0; v < 8; ++v) dG[v] = right ? -g[v] : t[v] - g[v];
-#pragma unroll
-    for (int v = 0; v < 8; ++v) dH[v] = hp[v] - hc[v];
-    if (front && right && !bottom) dF[EN] = f[EN] - f[EN];
+    for (int v = 0; v < 8; ++v) {
+        dF[v] = bottom ? -fc[v] : fxp[v] - fc[v];
+        dG[v] = right ? -gc[v] : gyp[v] - gc[v];
+        dH[v] = hp[v] - hc[v];
+    }
+    if (front && right && !bottom) dF[EN] = fc[EN] - fc[EN];
     if (front && bottom && !right) {
-        dH[MZ] = hp[MZ] - g[MZ];
-        dH[EN] = hp[EN] - g[EN];
-        dG[BZ] = t[BZ] - t[BZ];
+        dH[MZ] = hp[MZ] - gc[MZ];
+        dH[EN] = hp[EN] - gc[EN];
+        dG[BZ] = gyp[BZ] - gyp[BZ];
     }
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
@@ -108,12 +108,65 @@ __device__ __forceinline__ void qint_cell(const float c[8], const float xp[8], c
     }
 }
 
+// Predictor at one cell from raw states: c = Q(i,j,k), xp = Q(i+1,j,k), yp = Q(i,j+1,k), hc = H(Q(i,j,k)),
+// hp = H(Q(i,j,k+1)); xm, ym, zm, zp only when `lap`.
+template <int PATH>
+__device__ __forceinline__ void qint_cell(const float c[8], const float xp[8], const float yp[8], const float hc[8],
+                                          const float hp[8], const float xm[8], const float ym[8], const float zm[8],
+                                          const float zp[8], bool bottom, bool right, bool front, bool lap,
+                                          const Params& P, float out[8]) {
+    const Prim s = make_prim(c);
+    float f[8], g[8], fx[8], gy[8];
+    flux_idx<DIR_X>(c, s, f);
+    flux_idx<DIR_Y>(c, s, g);
+    flux_idx<DIR_X>(xp, make_prim(xp), fx);
+    flux_idx<DIR_Y>(yp, make_prim(yp), gy);
+    qint_combine<PATH>(c, f, fx, g, gy, hc, hp, xm, xp, ym, yp, zm, zp, bottom, right, front, lap, P, out);
+}
+
 // -----------------------------------------------------------------------------------------------
 // Corrector at one cell (fast recipe).  q = Q(i,j,k); c, xm, ym, zm = Qint at the cell and at
 // i-1, j-1, k-1; xp, yp, zp = Qint at i+1, j+1, k+1 (path B diffusion only).
 // kernels_od.cu:378-522 / :120-345, LaxWendroffAdv*Local :1206-1332, quirks B-4, B-5, B-6.
-// Must be called by all 32 lanes of a warp whose lanes hold consecutive j (LANES_I: consecutive i); it shuffles.
 // -----------------------------------------------------------------------------------------------
+// H'(Qint(i,j,k-1)) with the reference's mixed neighbours: Bsq from (Bx(i-1), By(j-1), Bz(k-1)) (B-4), Bdotu with
+// rhovy(j-1) (B-5); KE and the velocities from the k-1 state itself
+__device__ __forceinline__ void hflux_km1(const float zm[8], const float xm[8], const float ym[8], float hk[8]) {
+    Prim sk;
+    const float inv = fast_rcp(zm[RHO]);
+    sk.ux = zm[MX] * inv; sk.uy = zm[MY] * inv; sk.uz = zm[MZ] * inv;
+    sk.Bsq = fmaf(zm[BZ], zm[BZ], fmaf(ym[BY], ym[BY], xm[BX] * xm[BX]));
+    const float ke = fmaf(sk.uz, zm[MZ], fmaf(sk.uy, zm[MY], sk.ux * zm[MX]));
+    sk.p = kGm1f * fmaf(-0.5f, sk.Bsq, zm[EN] - ke);
+    sk.ptot = fmaf(0.5f, sk.Bsq, sk.p);
+    sk.Bdotu = fmaf(sk.uz, zm[BZ], fmaf(ym[MY] * inv, zm[BY], sk.ux * zm[BX]));
+    flux_loc<DIR_Z>(zm, sk, hk);
+}
+
+// From evaluated fluxes: fc, gc, hc = F', G', H' of Qint at the cell; fi = F'(Qint(i-1)), gj = G'(Qint(j-1)),
+// hk = hflux_km1.
+template <int PATH>
+__device__ __forceinline__ void corr_combine(const float q[8], const float c[8], const float fc[8], const float fi[8],
+                                             const float gc[8], const float gj[8], const float hc[8], const float hk[8],
+                                             const float xm[8], const float ym[8], const float zm[8], const float xp[8],
+                                             const float yp[8], const float zp[8], const Params& P, float out[8]) {
+    const float hx = 0.5f * P.tx, hy = 0.5f * P.ty, hz = 0.5f * P.tz;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        const float fim = (PATH == IMHD_PATH_B && v == RHO) ? xm[RHO] : fi[v];  // B-6
+        const float dF = fc[v] - fim, dG = gc[v] - gj[v], dH = hc[v] - hk[v];
+        // reference: float(0.5*(q+c) - 0.5tx dF - 0.5ty dG - 0.5tz dH) with q+c an fp32 sum and the rest
+        // fp64.  0.5*s is exact and T is ~1e-2 of it, so one fp32 rounding of (0.5 s - T) reproduces it.
+        const float s = q[v] + c[v];
+        const float T = fmaf(hx, dF, fmaf(hy, dG, hz * dH));
+        float r = fmaf(0.5f, s, -T);
+        if (PATH == IMHD_PATH_B) r = add_diffusion(r, c[v], xp[v], yp[v], zp[v], xm[v], ym[v], zm[v], P.dc);
+        out[v] = r;
+    }
+}
+
+// From raw states.  Must be called by all 32 lanes of a warp whose lanes hold consecutive j (LANES_I: consecutive
+// i); it shuffles.
 template <int PATH, bool LANES_I = false>
 __device__ __forceinline__ void corr_cell(const float q[8], const float c[8], const float xm[8], const float ym[8],
                                           const float zm[8], const float xp[8], const float yp[8], const float zp[8],
@@ -135,31 +188,8 @@ __device__ __forceinline__ void corr_cell(const float q[8], const float c[8], co
 #pragma unroll
         for (int v = 0; v < 8; ++v) gj[v] = v == BY ? 0.0f : __shfl_up_sync(0xffffffffu, gc[v], 1);
     }
-    {   // k-1 point with the reference's mixed neighbours: Bsq from (Bx(i-1), By(j-1), Bz(k-1)) (B-4), Bdotu with
-        // rhovy(j-1) (B-5); KE and the velocities from the k-1 state itself
-        Prim sk;
-        const float inv = fast_rcp(zm[RHO]);
-        sk.ux = zm[MX] * inv; sk.uy = zm[MY] * inv; sk.uz = zm[MZ] * inv;
-        sk.Bsq = fmaf(zm[BZ], zm[BZ], fmaf(ym[BY], ym[BY], xm[BX] * xm[BX]));
-        const float ke = fmaf(sk.uz, zm[MZ], fmaf(sk.uy, zm[MY], sk.ux * zm[MX]));
-        sk.p = kGm1f * fmaf(-0.5f, sk.Bsq, zm[EN] - ke);
-        sk.ptot = fmaf(0.5f, sk.Bsq, sk.p);
-        sk.Bdotu = fmaf(sk.uz, zm[BZ], fmaf(ym[MY] * inv, zm[BY], sk.ux * zm[BX]));
-        flux_loc<DIR_Z>(zm, sk, hk);
-    }
-    if (PATH == IMHD_PATH_B) fi[RHO] = xm[RHO];  // B-6
-    const float hx = 0.5f * P.tx, hy = 0.5f * P.ty, hz = 0.5f * P.tz;
-#pragma unroll
-    for (int v = 0; v < 8; ++v) {
-        const float dF = fc[v] - fi[v], dG = gc[v] - gj[v], dH = hc[v] - hk[v];
-        // reference: float(0.5*(q+c) - 0.5tx dF - 0.5ty dG - 0.5tz dH) with q+c an fp32 sum and the rest
-        // fp64.  0.5*s is exact and T is ~1e-2 of it, so one fp32 rounding of (0.5 s - T) reproduces it.
-        const float s = q[v] + c[v];
-        const float T = fmaf(hx, dF, fmaf(hy, dG, hz * dH));
-        float r = fmaf(0.5f, s, -T);
-        if (PATH == IMHD_PATH_B) r = add_diffusion(r, c[v], xp[v], yp[v], zp[v], xm[v], ym[v], zm[v], P.dc);
-        out[v] = r;
-    }
+    hflux_km1(zm, xm, ym, hk);
+    corr_combine<PATH>(q, c, fc, fi, gc, gj, hc, hk, xm, ym, zm, xp, yp, zp, P, out);
 }
 
 // Path B, k = 0 face (BoundaryConditions, kernels_fluidbcs.cu:52-116): corrector with INDEXED fluxes of
@@ -528,6 +558,299 @@ __global__ void __launch_bounds__(TI * 32, 1) k_fused_step_tma(const FusedArgs A
 }
 
 // -----------------------------------------------------------------------------------------------
+// The fused z-marching kernel, register-tiled rows (the hot path).  Same march, same TMA staging and
+// the same device functions as k_fused_step_tma, but every thread owns R consecutive rows (i) of one
+// column j, so that
+//   - F(Q) and F'(Qint) of a cell are evaluated once and reused as the i+1 / i-1 neighbour flux of the
+//     next row of the same thread (registers, no exchange),
+//   - the primitives of Q(k+1) are carried in the register queue from the iteration that evaluated
+//     H(Q(k+1)) instead of being re-derived,
+//   - only the first and the last row of a thread go through the Qint exchange array, and the x
+//     neighbours of the Laplacians inside the thread come from registers,
+//   - addressing, predicates, loop control and the barrier are paid once per R cells.
+// The thread tile is TI*R rows x 32 lanes: 8 warps x 2 rows give the 16x32 tile of the one-row kernel
+// with half the threads (255 registers each, no spills); 12 warps x 2 rows a 24x32 tile (22x30 outputs).
+// -----------------------------------------------------------------------------------------------
+template <int PATH, int TI, int R>
+struct RowsGeo {
+    static constexpr int NR = TI * R;                                   // rows of the thread tile
+    static constexpr int TR = NR + 2;                                   // tile rows (one ring row either side)
+    static constexpr int WI = PATH == IMHD_PATH_A ? NR - 1 : NR - 2;    // output rows per tile
+    static constexpr int WJ = PATH == IMHD_PATH_A ? 31 : 30;            // output lanes per tile
+    static constexpr int STAGE_FLOATS = 8 * TR * kTC;
+    static constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
+    static constexpr int XBUF = 2 * 8 * TI * 32;                        // one exchange buffer: [first,last][v][ti][lane]
+    static constexpr size_t SMEM = 3 * STAGE_BYTES + 2 * XBUF * 4 + 64;
+};
+
+template <int R>
+struct RowsThread {  // per-thread constants
+    unsigned rows;          // per row rr: bit rr = bottom, 8+rr = interior i, 16+rr = corrector-updated row, 24+rr = owner row
+    unsigned lanes;         // bit 0 = right, 1 = interior j, 2 = corrector-updated column, 3 = owner column
+    int own;                // tile offset of the cell of row 0
+    int xs, xsm, xsp;       // exchange slots: own, thread row above, thread row below
+    int i0, jc;             // row of rr = 0; column clamped into the domain
+    __device__ __forceinline__ bool bottom(int rr) const { return (rows >> rr) & 1u; }
+    __device__ __forceinline__ bool interior_i(int rr) const { return (rows >> (8 + rr)) & 1u; }
+    __device__ __forceinline__ bool upd_i(int rr) const { return (rows >> (16 + rr)) & 1u; }
+    __device__ __forceinline__ bool owner_i(int rr) const { return (rows >> (24 + rr)) & 1u; }
+    __device__ __forceinline__ bool right() const { return lanes & 1u; }
+    __device__ __forceinline__ bool interior_j() const { return lanes & 2u; }
+    __device__ __forceinline__ bool upd_j() const { return lanes & 4u; }
+    __device__ __forceinline__ bool owner_j() const { return lanes & 8u; }
+};
+
+// One plane of the march for the R rows of a thread: predictor plane k+1, corrector plane k.  Straight-line on
+// purpose: with 8 warps per SM every taken branch is an instruction-fetch bubble nobody hides, so the tile's ring
+// rows and the warm-up planes run the corrector too and only their STORES are predicated off (`store_ok`).
+template <int PATH, int TI, int R>
+__device__ __forceinline__ void rows_plane(const FusedArgs& A, const RowsThread<R>& T, bool hi, bool store_ok, const float* tq1,
+                                           const float* tq2, const float* xq, const float (&q0)[R][8],
+                                           const float (&q1)[R][8], float (&qn)[R][8], const float (&h1)[R][8],
+                                           float (&hn)[R][8], const Prim (&p1)[R], Prim (&pn)[R], const float (&qim)[R][8],
+                                           const float (&qic)[R][8], float (&qip)[R][8], float* outp) {
+    using G = RowsGeo<PATH, TI, R>;
+    const Params& P = A.P;
+    constexpr int VS = G::TR * kTC;   // variable stride inside a tile
+    constexpr int XV = TI * 32;       // variable stride inside an exchange buffer
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) qn[rr][v] = tq2[v * VS + T.own + rr * kTC];
+        pn[rr] = make_prim(qn[rr]);
+        flux_idx<DIR_Z>(qn[rr], pn[rr], hn[rr]);
+    }
+    // ---- predictor plane k+1 ---------------------------------------------------------------------------
+    {
+        float xlast[8], xfirst[8], fa[8], fb[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            xlast[v] = tq1[v * VS + T.own + R * kTC];                       // Q(k+1) one row below the thread's rows
+            if (PATH == IMHD_PATH_B) xfirst[v] = tq1[v * VS + T.own - kTC];  // ... and one row above
+        }
+        flux_idx<DIR_X>(q1[0], p1[0], fa);
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const float* xp = rr < R - 1 ? q1[rr + 1 < R ? rr + 1 : rr] : xlast;
+            const float* xm = rr > 0 ? q1[rr > 0 ? rr - 1 : 0] : xfirst;
+            if (rr < R - 1) flux_idx<DIR_X>(q1[rr + 1 < R ? rr + 1 : rr], p1[rr + 1 < R ? rr + 1 : rr], fb);
+            else            flux_idx<DIR_X>(xlast, make_prim(xlast), fb);
+            float g[8], gy[8], yp[8], ym[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                yp[v] = tq1[v * VS + T.own + rr * kTC + 1];
+                if (PATH == IMHD_PATH_B) ym[v] = tq1[v * VS + T.own + rr * kTC - 1];
+            }
+            flux_idx<DIR_Y>(q1[rr], p1[rr], g);
+            flux_idx<DIR_Y>(yp, make_prim(yp), gy);
+            qint_combine<PATH>(q1[rr], fa, fb, g, gy, h1[rr], hn[rr], xm, xp, ym, yp, q0[rr], qn[rr], T.bottom(rr),
+                               T.right(), false, T.interior_i(rr) && T.interior_j(), P, qip[rr]);
+#pragma unroll
+            for (int v = 0; v < 8; ++v) fa[v] = fb[v];
+        }
+    }
+    if (__builtin_expect(hi, 0)) {  // the plane above the slab comes from the neighbour (or is the periodic image): once per slab
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) ldg8(A.qhi, (long long)min(T.i0 + rr, P.Nx - 1) * P.Ny + T.jc, P.plane, qip[rr]);
+    }
+    // ---- corrector plane k -----------------------------------------------------------------------------
+    {
+        float xfirst[8], xlast[8], fa[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            xfirst[v] = xq[(8 + v) * XV + T.xsm];                          // Qint(k), last row of the thread row above
+            if (PATH == IMHD_PATH_B) xlast[v] = xq[v * XV + T.xsp];        // ... first row of the thread row below
+        }
+        flux_loc<DIR_X>(xfirst, make_prim(xfirst), fa);
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const float* c = qic[rr];
+            const Prim sc = make_prim(c);
+            const float* xm = rr > 0 ? qic[rr > 0 ? rr - 1 : 0] : xfirst;
+            const float* xp = rr < R - 1 ? qic[rr + 1 < R ? rr + 1 : rr] : xlast;
+            float fc[8], gc[8], hc[8], gj[8], hk[8], ym[8], yp[8], out[8];
+            flux_loc<DIR_X>(c, sc, fc);
+            flux_loc<DIR_Y>(c, sc, gc);
+            flux_loc<DIR_Z>(c, sc, hc);
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                ym[v] = __shfl_up_sync(0xffffffffu, c[v], 1);
+                if (PATH == IMHD_PATH_B) yp[v] = __shfl_down_sync(0xffffffffu, c[v], 1);
+                gj[v] = v == BY ? 0.0f : __shfl_up_sync(0xffffffffu, gc[v], 1);
+            }
+            hflux_km1(qim[rr], xm, ym, hk);
+            corr_combine<PATH>(q0[rr], c, fc, fa, gc, gj, hc, hk, xm, ym, qim[rr], xp, yp, qip[rr], P, out);
+            if (store_ok && T.owner_i(rr) && T.owner_j()) {
+                char* o = reinterpret_cast<char*>(outp + (long long)rr * P.Ny);
+                const bool upd = T.upd_i(rr) && T.upd_j();
+#pragma unroll
+                for (int v = 0; v < 8; ++v)  // untouched cells are carried over
+                    *reinterpret_cast<float*>(o + (unsigned long long)A.vs32 * (unsigned)(4 * v)) = upd ? out[v] : q0[rr][v];
+            }
+#pragma unroll
+            for (int v = 0; v < 8; ++v) fa[v] = fc[v];
+        }
+    }
+}
+
+// keeps a per-thread constant in its register: without this ptxas re-derives it from S2R / LDC every plane
+__device__ __forceinline__ void keep(int& x) { asm volatile("" : "+r"(x)); }
+__device__ __forceinline__ void keep(unsigned& x) { asm volatile("" : "+r"(x)); }
+
+template <int PATH, int TI, int R, bool ROLLED>
+__global__ void __launch_bounds__(TI * 32, 1) k_fused_rows(const FusedArgs A, const __grid_constant__ CUtensorMap tmap) {
+    using G = RowsGeo<PATH, TI, R>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* tiles = reinterpret_cast<float*>(smem_raw);                       // [3][8][TR][kTC]
+    float* xch = tiles + 3 * G::STAGE_FLOATS;                                 // [2][first,last][8][TI][32]  Qint exchange
+    uint64_t* full = reinterpret_cast<uint64_t*>(xch + 2 * G::XBUF);          // [3]
+
+    const Params& P = A.P;
+    const int lane = threadIdx.x, ti = threadIdx.y;
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    const int ib = bi * G::WI, jb = bj * G::WJ;
+    const int t0 = ti * R, i0 = ib + t0, j = jb + lane;
+    const int oi_lo = bi == 0 ? 0 : ib + 1, oi_hi = bi == A.ntile_i - 1 ? P.Nx : ib + G::WI + 1;
+    const int oj_lo = bj == 0 ? 0 : jb + 1, oj_hi = bj == A.ntile_j - 1 ? P.Ny : jb + G::WJ + 1;
+    RowsThread<R> T;
+    T.rows = 0;
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+        const int i = i0 + rr, t = t0 + rr;
+        const bool corr_row = t >= 1 && (PATH == IMHD_PATH_A || t <= G::NR - 2);  // rows with valid Qint neighbours
+        if (i == P.Nx - 1) T.rows |= 1u << rr;
+        if (i > 0 && i < P.Nx - 1) T.rows |= 1u << (8 + rr);
+        if (corr_row && i > 0 && (PATH == IMHD_PATH_A ? i < P.Nx : i < P.Nx - 1)) T.rows |= 1u << (16 + rr);
+        if (i < P.Nx && i >= oi_lo && i < oi_hi) T.rows |= 1u << (24 + rr);
+    }
+    const bool interior_j = j > 0 && j < P.Ny - 1;
+    T.lanes = (j == P.Ny - 1 ? 1u : 0u) | (interior_j ? 2u : 0u) |
+              ((PATH == IMHD_PATH_A ? (j > 0 && j < P.Ny) : interior_j) ? 4u : 0u) | ((j < P.Ny && j >= oj_lo && j < oj_hi) ? 8u : 0u);
+    // the box starts at the 4-column boundary at or below jb-1 (measured: a misaligned inner coordinate traps)
+    const int c0 = ((jb - 1 + 4) / 4) * 4 - 4;
+    T.own = (t0 + 1) * kTC + (jb - 1 - c0) + lane + 1;
+    T.xs = ti * 32 + lane;
+    T.xsm = max(ti - 1, 0) * 32 + lane;
+    T.xsp = min(ti + 1, TI - 1) * 32 + lane;
+    T.i0 = i0;
+    T.jc = min(j, P.Ny - 1);
+    keep(T.rows); keep(T.lanes); keep(T.own); keep(T.xs); keep(T.xsm); keep(T.xsp);
+
+    const int ka = A.kfrom + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kto);
+    const bool first = ka == A.ka0;  // the plane below is the slab's qint_lo; otherwise re-derive it in a warm-up plane
+    const int ks = first ? ka - 1 : ka - 2;
+    const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
+    const int klast = kb + 1;  // last plane any iteration reads
+
+    auto issue = [&](int plane, int stage) {  // producer only
+        const int kc = min(max(plane, A.kmin), A.kmax) - A.kbase;
+        mbar_expect_tx(&full[stage], G::STAGE_BYTES);
+        tma_load_tile(tiles + stage * G::STAGE_FLOATS, &tmap, &full[stage], c0, ib - 1, kc);
+    };
+
+    if (producer) {
+        for (int s = 0; s < 3; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+    if (producer)
+        for (int s = 0; s < 3; ++s) issue(ks + s, s);
+
+    float qa[R][8], qb[R][8], qc[R][8], ha[R][8], hb[R][8], hc[R][8], ia[R][8], ib_[R][8], ic[R][8];
+    Prim pa[R], pb[R], pc[R];
+    constexpr int VS = G::TR * kTC;
+    mbar_wait(&full[0], 0);
+    mbar_wait(&full[1], 0);
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            qa[rr][v] = tiles[v * VS + T.own + rr * kTC];
+            qb[rr][v] = tiles[G::STAGE_FLOATS + v * VS + T.own + rr * kTC];
+            ia[rr][v] = 1.0f;
+            ib_[rr][v] = 1.0f;
+        }
+        pb[rr] = make_prim(qb[rr]);
+        flux_idx<DIR_Z>(qb[rr], pb[rr], hb[rr]);
+        // Qint(ka-1); rows beyond the domain read the last row (they never produce output)
+        if (first) ldg8(A.qlo, (long long)min(i0 + rr, P.Nx - 1) * P.Ny + T.jc, P.plane, ib_[rr]);
+    }
+
+    // output pointer of row 0 at plane ks; stores are predicated off below plane ka
+    float* outp = A.Qout + (long long)(ks - A.kbase) * P.plane + (long long)i0 * P.Ny + T.jc;
+    int xsel = 0;  // exchange buffer of this plane (floats): alternates between 0 and XBUF
+    int k = ks;
+
+    if (ROLLED) {
+        // one copy of the plane body (fits the instruction cache); the register queue rotates by moves
+        int s2 = 2;         // stage of plane k+2, and the parity of its next mbarrier phase
+        uint32_t par = 0;   // bit s = parity of the next wait on stage s: stages 0,1 were waited once in the prologue
+        par = 0x3;
+#pragma unroll 1
+        for (; k < kb; ++k) {
+            const int s1 = s2 == 0 ? 2 : s2 - 1, sfree = s1 == 0 ? 2 : s1 - 1;
+            float* xq = xch + xsel;
+            xsel ^= G::XBUF;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                xq[v * TI * 32 + T.xs] = ib_[0][v];
+                xq[(8 + v) * TI * 32 + T.xs] = ib_[R - 1][v];
+            }
+            mbar_wait(&full[s2], (par >> s2) & 1u);
+            par ^= 1u << s2;
+            __syncthreads();
+            if (producer && k + 3 <= klast) issue(k + 3, sfree);
+            rows_plane<PATH, TI, R>(A, T, k + 1 == A.hi_plane, k >= ka, tiles + s1 * G::STAGE_FLOATS, tiles + s2 * G::STAGE_FLOATS, xq,
+                                    qa, qb, qc, hb, hc, pb, pc, ia, ib_, ic, outp);
+            outp += P.plane;
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    qa[rr][v] = qb[rr][v]; qb[rr][v] = qc[rr][v]; hb[rr][v] = hc[rr][v];
+                    ia[rr][v] = ib_[rr][v]; ib_[rr][v] = ic[rr][v];
+                }
+                pb[rr] = pc[rr];
+            }
+            s2 = s2 == 2 ? 0 : s2 + 1;
+        }
+        return;
+    }
+
+    float* t0p = tiles;
+    float* t1p = tiles + G::STAGE_FLOATS;
+    float* t2p = tiles + 2 * G::STAGE_FLOATS;
+    // one step of the march; roles (Q(k),Q(k+1),Q(k+2)) and their H / primitives, (Qint(k-1),Qint(k),Qint(k+1)) and the
+    // three tile stages rotate by renaming (period 3); the exchange buffer alternates at run time
+#define IMHD_ROWS_MARCH(Q0, Q1, QN, H1, HN, P1, PN, IM, IC, IP, TQ1, TQ2, SFREE, S2)                                   \
+    if (k < kb) {                                                                                                     \
+        float* xq = xch + xsel;                                                                                       \
+        xsel ^= G::XBUF;                                                                                              \
+        _Pragma("unroll") for (int v = 0; v < 8; ++v) {                                                               \
+            xq[v * TI * 32 + T.xs] = IC[0][v];                                                                        \
+            xq[(8 + v) * TI * 32 + T.xs] = IC[R - 1][v];                                                              \
+        }                                                                                                             \
+        mbar_wait(&full[S2], par##S2);                                                                                \
+        par##S2 ^= 1;                                                                                                 \
+        __syncthreads();                                                                                              \
+        if (producer && k + 3 <= klast) issue(k + 3, SFREE);                                                          \
+        rows_plane<PATH, TI, R>(A, T, k + 1 == A.hi_plane, k >= ka, TQ1, TQ2, xq, Q0, Q1, QN, H1, HN, P1, PN, IM, IC, IP, outp); \
+        outp += P.plane;                                                                                              \
+        ++k;                                                                                                          \
+    }
+
+    // parity of the NEXT wait on each stage: stages 0,1 were waited once in the prologue
+    uint32_t par0 = 1, par1 = 1, par2 = 0;
+    while (k < kb) {
+        IMHD_ROWS_MARCH(qa, qb, qc, hb, hc, pb, pc, ia, ib_, ic, t1p, t2p, 0, 2)
+        IMHD_ROWS_MARCH(qb, qc, qa, hc, ha, pc, pa, ib_, ic, ia, t2p, t0p, 1, 0)
+        IMHD_ROWS_MARCH(qc, qa, qb, ha, hb, pa, pb, ic, ia, ib_, t0p, t1p, 2, 1)
+    }
+#undef IMHD_ROWS_MARCH
+}
+
+// -----------------------------------------------------------------------------------------------
 // Remainder strip.  The tiles of the hot kernel produce 30 (path A: 31) output columns each; when Ny leaves a
 // remainder of a few columns (304 -> 10 x 30 + 2) a whole extra tile column -- 9 % of the launch at 304 -- would
 // compute them with 2 of 32 lanes.  This kernel takes the last columns instead, TRANSPOSED: lanes run along i and
@@ -788,6 +1111,8 @@ static int fill_args(FusedArgs& A, const float* Qin, float* Qout, const float* q
     A.Qin = Qin; A.Qout = Qout;
     const int g = s->ghosts ? 1 : 0;
     A.vs = (long long)(s->nzl + 2 * g) * A.P.plane;
+    if (A.vs >= (1ll << 32)) { set_error("slab of %lld cells per variable exceeds the 2^32 addressing range", A.vs); return IMHD_E_INVALID; }
+    A.vs32 = (unsigned)A.vs;
     A.kbase = s->k0 - g;
     A.kmin = max(s->k0 - g, 0);
     A.kmax = min(s->k0 + s->nzl - 1 + g, s->Nz - 1);
@@ -844,9 +1169,9 @@ static PFN_cuTensorMapEncodeTiled get_encode() {
     return fn;
 }
 
-static int g_force_ldg = 0, g_no_strip = 0, g_force_strip = 0;
+static int g_force_ldg = 0, g_no_strip = 0, g_force_strip = 0, g_kernel = 0;
 extern "C" void imhd_set_kernel_variant(int flags) {
-    g_force_ldg = flags & 1; g_no_strip = (flags >> 1) & 1; g_force_strip = (flags >> 2) & 1;
+    g_force_ldg = flags & 1; g_no_strip = (flags >> 1) & 1; g_force_strip = (flags >> 2) & 1; g_kernel = (flags >> 4) & 15;
 }
 
 // 4-D view (j, i, plane, variable) of a state array for the tile loads of the TMA kernel.
@@ -901,59 +1226,92 @@ static int pick_chunk(FusedArgs& A, int nz, long long tiles = 0) {
     return (nz + chunk - 1) / chunk;
 }
 
+// The one-row kernel and the register-tiled kernels share the launch logic: tile counts from the geometry, the
+// remainder strip, wave-aware z-chunks.
 template <int PATH, int TI>
+struct OneRowLaunch {
+    using G = TmaGeo<PATH, TI>;
+    static constexpr int THREAD_ROWS = TI;
+    static auto kernel() { return k_fused_step_tma<PATH, TI>; }
+};
+template <int PATH, int TI, int R, bool ROLLED>
+struct RowsLaunch {
+    using G = RowsGeo<PATH, TI, R>;
+    static constexpr int THREAD_ROWS = TI;
+    static auto kernel() { return k_fused_rows<PATH, TI, R, ROLLED>; }
+};
+
+template <int PATH, class L>
+static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, cudaStream_t st) {
+    using G = typename L::G;
+    const Params& P = A.P;
+    const int nz = A.kto - A.kfrom;
+    const int ni = PATH == IMHD_PATH_A ? P.Nx - 1 : P.Nx - 2, nj = PATH == IMHD_PATH_A ? P.Ny - 1 : P.Ny - 2;
+    A.ntile_i = (ni + G::WI - 1) / G::WI;
+    A.ntile_j = (nj + G::WJ - 1) / G::WJ;
+    // a remainder of a few columns goes to the transposed strip kernel instead of a whole extra tile column
+    constexpr int O = Ring<PATH>::O;
+    const int rem = nj % G::WJ;
+    const int strip_rows = PATH == IMHD_PATH_A ? 1 + rem : 1 + rem + 1;  // predictor-only ring row, outputs (, wall column)
+    // (not for short plane ranges such as the slab-end launches of the multi-GPU loop: there the strip's fixed
+    // latency costs more than the extra tile column; the test hook bit 2 forces it on for any length)
+    const bool strip = !g_no_strip && rem > 0 && strip_rows <= kStripRows && nj / G::WJ >= 2 && (nz >= 64 || g_force_strip);
+    int grid_j = A.ntile_j;
+    if (strip) {
+        grid_j = nj / G::WJ;
+        A.ntile_j = grid_j + 1;  // no hot-kernel tile is the last one: none widens its window to the domain edge
+    }
+    const int nchunk = pick_chunk(A, nz, (long long)A.ntile_i * grid_j);
+    static unsigned long long done = 0;
+    if (int e = ensure_smem(L::kernel(), G::SMEM, done)) return e;
+    L::kernel()<<<dim3(grid_j, A.ntile_i, nchunk), dim3(32, L::THREAD_ROWS), G::SMEM, st>>>(A, tmap);
+    IMHD_LAUNCH_CHECK(1);
+    if (strip) {
+        FusedArgs S = A;
+        constexpr int WL = 32 - 2 * O;
+        S.ntile_i = (ni + WL - 1) / WL;
+        S.jstrip = grid_j * G::WJ - 1;          // tile column 0; the ring row sits at jstrip + 1 = the last hot-kernel output
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int n = (3 * sms + S.ntile_i - 1) / S.ntile_i;      // a few small blocks per SM
+        n = n > nz / 8 ? nz / 8 : n;
+        n = n < 1 ? 1 : n;
+        S.chunk = (nz + n - 1) / n;
+        if (g_chunk_override > 0) S.chunk = g_chunk_override;
+        S.chunk = S.chunk < 2 ? 2 : (S.chunk > nz ? nz : S.chunk);
+        constexpr size_t strip_smem = (2 * 8 * kStripRows * 32 + 4 * 8 * 32 * (kStripCols + 1)) * sizeof(float);
+        static unsigned long long sdone = 0;
+        if (int e = ensure_smem(k_fused_strip<PATH>, strip_smem, sdone)) return e;
+        k_fused_strip<PATH><<<dim3(S.ntile_i, 1, (nz + S.chunk - 1) / S.chunk), dim3(32, strip_rows), strip_smem, st>>>(S);
+        IMHD_LAUNCH_CHECK(1);
+    }
+    return 0;
+}
+
+template <int PATH>
 static int launch_fused(FusedArgs& A, int nplanes_array, cudaStream_t st) {
     const Params& P = A.P;
     const int nz = A.kto - A.kfrom;
     if (nz <= 0) return 0;
-    // cells the corrector updates, counted from index 1: i in [1, Nx-1] (A) / [1, Nx-2] (B); edge cells ride along
-    const int ni = PATH == IMHD_PATH_A ? P.Nx - 1 : P.Nx - 2, nj = PATH == IMHD_PATH_A ? P.Ny - 1 : P.Ny - 2;
     CUtensorMap tmap;
-    if (make_tile_map(&tmap, A, nplanes_array, TmaGeo<PATH, TI>::TR)) {
-        using G = TmaGeo<PATH, TI>;
-        A.ntile_i = (ni + G::WI - 1) / G::WI;
-        A.ntile_j = (nj + G::WJ - 1) / G::WJ;
-        // a remainder of a few columns goes to the transposed strip kernel instead of a whole extra tile column
-        constexpr int O = Ring<PATH>::O;
-        const int rem = nj % G::WJ;
-        const int strip_rows = PATH == IMHD_PATH_A ? 1 + rem : 1 + rem + 1;  // predictor-only ring row, outputs (, wall column)
-        // (not for short plane ranges such as the slab-end launches of the multi-GPU loop: there the strip's fixed
-        // latency costs more than the extra tile column; the test hook bit 2 forces it on for any length)
-        const bool strip = !g_no_strip && rem > 0 && strip_rows <= kStripRows && nj / G::WJ >= 2 && (nz >= 64 || g_force_strip);
-        int grid_j = A.ntile_j;
-        if (strip) {
-            grid_j = nj / G::WJ;
-            A.ntile_j = grid_j + 1;  // no hot-kernel tile is the last one: none widens its window to the domain edge
-        }
-        const int nchunk = pick_chunk(A, nz, (long long)A.ntile_i * grid_j);
-        static unsigned long long done = 0;
-        if (int e = ensure_smem(k_fused_step_tma<PATH, TI>, G::SMEM, done)) return e;
-        k_fused_step_tma<PATH, TI><<<dim3(grid_j, A.ntile_i, nchunk), dim3(32, TI), G::SMEM, st>>>(A, tmap);
-        IMHD_LAUNCH_CHECK(1);
-        if (strip) {
-            FusedArgs S = A;
-            constexpr int WL = 32 - 2 * O;
-            S.ntile_i = (ni + WL - 1) / WL;
-            S.jstrip = grid_j * G::WJ - 1;          // tile column 0; the ring row sits at jstrip + 1 = the last hot-kernel output
-            int dev = 0, sms = 148;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            int n = (3 * sms + S.ntile_i - 1) / S.ntile_i;      // a few small blocks per SM
-            n = n > nz / 8 ? nz / 8 : n;
-            n = n < 1 ? 1 : n;
-            S.chunk = (nz + n - 1) / n;
-            if (g_chunk_override > 0) S.chunk = g_chunk_override;
-            S.chunk = S.chunk < 2 ? 2 : (S.chunk > nz ? nz : S.chunk);
-            constexpr size_t strip_smem = (2 * 8 * kStripRows * 32 + 4 * 8 * 32 * (kStripCols + 1)) * sizeof(float);
-            static unsigned long long sdone = 0;
-            if (int e = ensure_smem(k_fused_strip<PATH>, strip_smem, sdone)) return e;
-            k_fused_strip<PATH><<<dim3(S.ntile_i, 1, (nz + S.chunk - 1) / S.chunk), dim3(32, strip_rows), strip_smem, st>>>(S);
-            IMHD_LAUNCH_CHECK(1);
-        }
-        return 0;
+    // kernel choice (imhd_set_kernel_variant bits 4..7): 0 = default
+    switch (g_kernel) {
+        case 1:
+            if (make_tile_map(&tmap, A, nplanes_array, TmaGeo<PATH, 16>::TR)) return launch_tma<PATH, OneRowLaunch<PATH, 16>>(A, tmap, st);
+            break;
+        case 2:
+            if (make_tile_map(&tmap, A, nplanes_array, RowsGeo<PATH, 8, 2>::TR)) return launch_tma<PATH, RowsLaunch<PATH, 8, 2, true>>(A, tmap, st);
+            break;
+        default:
+            if (make_tile_map(&tmap, A, nplanes_array, RowsGeo<PATH, 8, 2>::TR)) return launch_tma<PATH, RowsLaunch<PATH, 8, 2, false>>(A, tmap, st);
+            break;
     }
+    constexpr int TI = 16;
     constexpr int O = Ring<PATH>::O;
     constexpr int WI = TI - 2 * O, WJ = 32 - 2 * O;
+    // cells the corrector updates, counted from index 1: i in [1, Nx-1] (A) / [1, Nx-2] (B); edge cells ride along
+    const int ni = PATH == IMHD_PATH_A ? P.Nx - 1 : P.Nx - 2, nj = PATH == IMHD_PATH_A ? P.Ny - 1 : P.Ny - 2;
     A.ntile_i = (ni + WI - 1) / WI;
     A.ntile_j = (nj + WJ - 1) / WJ;
     const int nchunk = pick_chunk(A, nz);
@@ -986,7 +1344,7 @@ extern "C" int imhd_step_fused_planes(const float* Qin, float* Qout, const float
     const Params& P = A.P;
     const unsigned pb = (unsigned)((P.plane + 255) / 256);
     if (s->path == IMHD_PATH_A) {
-        if (int e = launch_fused<IMHD_PATH_A, 16>(A, s->nzl + 2 * (s->ghosts ? 1 : 0), st)) return e;
+        if (int e = launch_fused<IMHD_PATH_A>(A, s->nzl + 2 * (s->ghosts ? 1 : 0), st)) return e;
         if (A.k0 == 0 && A.k1 == P.Nz && do_back) {  // PBCs on one GPU; across slabs the ghost exchange carries this plane
             k_plane_copy<<<pb, 256, 0, st>>>(Qout, (long long)(0 - A.kbase) * P.plane, (long long)(P.Nz - 1 - A.kbase) * P.plane,
                                              P.plane, A.vs);
@@ -994,7 +1352,7 @@ extern "C" int imhd_step_fused_planes(const float* Qin, float* Qout, const float
         }
         return 0;
     }
-    if (int e = launch_fused<IMHD_PATH_B, 16>(A, s->nzl + 2 * (s->ghosts ? 1 : 0), st)) return e;
+    if (int e = launch_fused<IMHD_PATH_B>(A, s->nzl + 2 * (s->ghosts ? 1 : 0), st)) return e;
     if (do_front) {
         k_front_plane_B<<<dim3((P.Ny + 31) / 32, (P.Nx + 7) / 8), dim3(32, 8), 0, st>>>(A);
         IMHD_LAUNCH_CHECK(1);
