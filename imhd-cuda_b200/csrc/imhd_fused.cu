@@ -70,97 +70,94 @@ __device__ __forceinline__ void ldg8(const float* __restrict__ A, long long off,
 __device__ __forceinline__ void hflux(const float U[8], float h[8]) { flux_idx<DIR_Z>(U, make_prim(U), h); }
 
 // -----------------------------------------------------------------------------------------------
-// Predictor at one cell (fast recipe), from fluxes that are already evaluated -- so a caller that
-// holds the neighbour's flux (register-tiled rows, shuffles) does not derive it twice:
-//   c = Q(i,j,k);  fc, fxp = F(Q) at the cell and at i+1;  gc, gyp = G(Q) at the cell and at j+1;
-//   hc, hp = H(Q) at the cell and at k+1;  xm..zp = the six neighbours of c (only when `lap`).
-// Cell classes and typos: kernels_od_intvar.cu:1160-1253, kernels_intvarbcs.cu:560-1110 (B-15).
+// Predictor (fast recipe) from evaluated fluxes, generic over the value type (imhd_math.cuh: float = one cell,
+// float2 = the two rows of a register-tiled thread):
+//   c = Q(i,j,k);  dF = F(Q(i+1)) - F(Q(i)) (the caller forms it: inside a register-tiled thread the i+1 flux is the
+//   next row's own flux; `bottom` cells pass -F);  gc, gyp = G(Q) at the cell and at j+1;  hc, hp = H(Q) at the cell
+//   and at k+1;  xsum = Q(i+1) + Q(i-1), ym, yp, zm, zp = the other neighbours of c (only where `lap`).
+// Cell classes: kernels_od_intvar.cu:1160-1253, kernels_intvarbcs.cu:560-1110.
 // -----------------------------------------------------------------------------------------------
-template <int PATH>
-__device__ __forceinline__ void qint_combine(const float c[8], const float fc[8], const float fxp[8], const float gc[8],
-                                             const float gyp[8], const float hc[8], const float hp[8], const float xm[8],
-                                             const float xp[8], const float ym[8], const float yp[8], const float zm[8],
-                                             const float zp[8], bool bottom, bool right, bool front, bool lap,
-                                             const Params& P, float out[8]) {
-    float dF[8], dG[8], dH[8];
+template <int PATH, class V>
+__device__ __forceinline__ void qint_combine(const V c[8], const V dF[8], const V gc[8], const V gyp[8], const V hc[8],
+                                             const V hp[8], const V xsum[8], const V ym[8], const V yp[8], const V zm[8],
+                                             const V zp[8], FlagT<V> bottom, FlagT<V> right, FlagT<V> lap, const Params& P,
+                                             V out[8]) {
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
-        dF[v] = bottom ? -fc[v] : fxp[v] - fc[v];
-        dG[v] = right ? -gc[v] : gyp[v] - gc[v];
-        dH[v] = hp[v] - hc[v];
-    }
-    if (front && right && !bottom) dF[EN] = fc[EN] - fc[EN];
-    if (front && bottom && !right) {
-        dH[MZ] = hp[MZ] - gc[MZ];
-        dH[EN] = hp[EN] - gc[EN];
-        dG[BZ] = gyp[BZ] - gyp[BZ];
-    }
-#pragma unroll
-    for (int v = 0; v < 8; ++v) {
-        float base = c[v];
-        if (v == MZ && bottom && right) base = c[MX];
-        float r = fmaf(-P.tz, dH[v], fmaf(-P.ty, dG[v], fmaf(-P.tx, dF[v], base)));
-        if (PATH == IMHD_PATH_B) {
-            const float rd = add_diffusion(r, c[v], xp[v], yp[v], zp[v], xm[v], ym[v], zm[v], P.dc);
-            r = lap ? rd : r;
-        }
+        const V dG = vsel(right, vneg(gc[v]), vsub(gyp[v], gc[v]));
+        const V dH = vsub(hp[v], hc[v]);
+        V base = c[v];
+        if (v == MZ) base = vsel(fand(bottom, right), c[MX], c[MZ]);  // intRhoVZBottomRight starts from the rhovx slot (B-15)
+        V r = vfmac(-P.tz, dH, vfmac(-P.ty, dG, vfmac(-P.tx, dF[v], base)));
+        if (PATH == IMHD_PATH_B) r = vsel(lap, add_diffusion(r, c[v], xsum[v], vadd(yp[v], ym[v]), vadd(zp[v], zm[v]), P.dc), r);
         out[v] = r;
     }
 }
 
 // Predictor at one cell from raw states: c = Q(i,j,k), xp = Q(i+1,j,k), yp = Q(i,j+1,k), hc = H(Q(i,j,k)),
-// hp = H(Q(i,j,k+1)); xm, ym, zm, zp only when `lap`.
+// hp = H(Q(i,j,k+1)); xm, ym, zm, zp only when `lap`.  `front` = the k = 0 edge lines with their typos (B-15).
 template <int PATH>
 __device__ __forceinline__ void qint_cell(const float c[8], const float xp[8], const float yp[8], const float hc[8],
                                           const float hp[8], const float xm[8], const float ym[8], const float zm[8],
                                           const float zp[8], bool bottom, bool right, bool front, bool lap,
                                           const Params& P, float out[8]) {
     const Prim s = make_prim(c);
-    float f[8], g[8], fx[8], gy[8];
+    float f[8], g[8], fx[8], gy[8], dF[8], xsum[8], hcc[8];
     flux_idx<DIR_X>(c, s, f);
     flux_idx<DIR_Y>(c, s, g);
     flux_idx<DIR_X>(xp, make_prim(xp), fx);
     flux_idx<DIR_Y>(yp, make_prim(yp), gy);
-    qint_combine<PATH>(c, f, fx, g, gy, hc, hp, xm, xp, ym, yp, zm, zp, bottom, right, front, lap, P, out);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        dF[v] = bottom ? -f[v] : fx[v] - f[v];
+        xsum[v] = PATH == IMHD_PATH_B ? xp[v] + xm[v] : 0.0f;
+        hcc[v] = hc[v];
+    }
+    if (front && right && !bottom) dF[EN] = f[EN] - f[EN];   // intEFrontRight: x difference == 0
+    if (front && bottom && !right) {                         // int{RhoVZ,E}FrontBottom subtract a Y flux in the z difference,
+        hcc[MZ] = g[MZ];                                     // intBZFrontBottom has a null y difference
+        hcc[EN] = g[EN];
+        g[BZ] = gy[BZ];
+    }
+    qint_combine<PATH, float>(c, dF, g, gy, hcc, hp, xsum, ym, yp, zm, zp, {bottom}, {right}, {lap}, P, out);
 }
 
 // -----------------------------------------------------------------------------------------------
-// Corrector at one cell (fast recipe).  q = Q(i,j,k); c, xm, ym, zm = Qint at the cell and at
-// i-1, j-1, k-1; xp, yp, zp = Qint at i+1, j+1, k+1 (path B diffusion only).
+// Corrector (fast recipe).  q = Q(i,j,k); c, xm, ym, zm = Qint at the cell and at i-1, j-1, k-1; xp, yp, zp = Qint at
+// i+1, j+1, k+1 (path B diffusion only).
 // kernels_od.cu:378-522 / :120-345, LaxWendroffAdv*Local :1206-1332, quirks B-4, B-5, B-6.
 // -----------------------------------------------------------------------------------------------
 // H'(Qint(i,j,k-1)) with the reference's mixed neighbours: Bsq from (Bx(i-1), By(j-1), Bz(k-1)) (B-4), Bdotu with
 // rhovy(j-1) (B-5); KE and the velocities from the k-1 state itself
-__device__ __forceinline__ void hflux_km1(const float zm[8], const float xm[8], const float ym[8], float hk[8]) {
-    Prim sk;
-    const float inv = fast_rcp(zm[RHO]);
-    sk.ux = zm[MX] * inv; sk.uy = zm[MY] * inv; sk.uz = zm[MZ] * inv;
-    sk.Bsq = fmaf(zm[BZ], zm[BZ], fmaf(ym[BY], ym[BY], xm[BX] * xm[BX]));
-    const float ke = fmaf(sk.uz, zm[MZ], fmaf(sk.uy, zm[MY], sk.ux * zm[MX]));
-    sk.p = kGm1f * fmaf(-0.5f, sk.Bsq, zm[EN] - ke);
-    sk.ptot = fmaf(0.5f, sk.Bsq, sk.p);
-    sk.Bdotu = fmaf(sk.uz, zm[BZ], fmaf(ym[MY] * inv, zm[BY], sk.ux * zm[BX]));
+template <class V>
+__device__ __forceinline__ void hflux_km1(const V zm[8], V xmBX, V ymBY, V ymMY, V hk[8]) {
+    PrimT<V> sk;
+    const V inv = vrcp(zm[RHO]);
+    sk.ux = vmul(zm[MX], inv); sk.uy = vmul(zm[MY], inv); sk.uz = vmul(zm[MZ], inv);
+    sk.Bsq = vfma(zm[BZ], zm[BZ], vfma(ymBY, ymBY, vmul(xmBX, xmBX)));
+    const V ke = vfma3(sk.uz, zm[MZ], vfma3(sk.uy, zm[MY], vmul(sk.ux, zm[MX])));
+    sk.p = vmulc(kGm1f, vfmac(-0.5f, sk.Bsq, vsub(zm[EN], ke)));
+    sk.ptot = vfmac(0.5f, sk.Bsq, sk.p);
+    sk.Bdotu = vfma3(sk.uz, zm[BZ], vfma3(vmul(ymMY, inv), zm[BY], vmul(sk.ux, zm[BX])));
     flux_loc<DIR_Z>(zm, sk, hk);
 }
 
-// From evaluated fluxes: fc, gc, hc = F', G', H' of Qint at the cell; fi = F'(Qint(i-1)), gj = G'(Qint(j-1)),
-// hk = hflux_km1.
-template <int PATH>
-__device__ __forceinline__ void corr_combine(const float q[8], const float c[8], const float fc[8], const float fi[8],
-                                             const float gc[8], const float gj[8], const float hc[8], const float hk[8],
-                                             const float xm[8], const float ym[8], const float zm[8], const float xp[8],
-                                             const float yp[8], const float zp[8], const Params& P, float out[8]) {
+// From evaluated fluxes: dF = F'(Qint(i)) - F'(Qint(i-1)) (formed by the caller, with B-6), gc, hc = G', H' of Qint at
+// the cell; gj = G'(Qint(j-1)), hk = hflux_km1; xsum = Qint(i+1) + Qint(i-1).
+template <int PATH, class V>
+__device__ __forceinline__ void corr_combine(const V q[8], const V c[8], const V dF[8], const V gc[8], const V gj[8],
+                                             const V hc[8], const V hk[8], const V xsum[8], const V ym[8], const V yp[8],
+                                             const V zm[8], const V zp[8], const Params& P, V out[8]) {
     const float hx = 0.5f * P.tx, hy = 0.5f * P.ty, hz = 0.5f * P.tz;
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
-        const float fim = (PATH == IMHD_PATH_B && v == RHO) ? xm[RHO] : fi[v];  // B-6
-        const float dF = fc[v] - fim, dG = gc[v] - gj[v], dH = hc[v] - hk[v];
+        const V dG = vsub(gc[v], gj[v]), dH = vsub(hc[v], hk[v]);
         // reference: float(0.5*(q+c) - 0.5tx dF - 0.5ty dG - 0.5tz dH) with q+c an fp32 sum and the rest
         // fp64.  0.5*s is exact and T is ~1e-2 of it, so one fp32 rounding of (0.5 s - T) reproduces it.
-        const float s = q[v] + c[v];
-        const float T = fmaf(hx, dF, fmaf(hy, dG, hz * dH));
-        float r = fmaf(0.5f, s, -T);
-        if (PATH == IMHD_PATH_B) r = add_diffusion(r, c[v], xp[v], yp[v], zp[v], xm[v], ym[v], zm[v], P.dc);
+        const V s = vadd(q[v], c[v]);
+        const V T = vfmac(hx, dF[v], vfmac(hy, dG, vmulc(hz, dH)));
+        V r = vfmac(0.5f, s, vneg(T));
+        if (PATH == IMHD_PATH_B) r = add_diffusion(r, c[v], xsum[v], vadd(yp[v], ym[v]), vadd(zp[v], zm[v]), P.dc);
         out[v] = r;
     }
 }
@@ -172,7 +169,7 @@ __device__ __forceinline__ void corr_cell(const float q[8], const float c[8], co
                                           const float zm[8], const float xp[8], const float yp[8], const float zp[8],
                                           const Params& P, float out[8]) {
     const Prim sc = make_prim(c);
-    float fc[8], gc[8], hc[8], fi[8], gj[8], hk[8];
+    float fc[8], gc[8], hc[8], fi[8], gj[8], hk[8], dF[8], xsum[8];
     flux_loc<DIR_X>(c, sc, fc);
     flux_loc<DIR_Y>(c, sc, gc);
     flux_loc<DIR_Z>(c, sc, hc);
@@ -188,8 +185,14 @@ __device__ __forceinline__ void corr_cell(const float q[8], const float c[8], co
 #pragma unroll
         for (int v = 0; v < 8; ++v) gj[v] = v == BY ? 0.0f : __shfl_up_sync(0xffffffffu, gc[v], 1);
     }
-    hflux_km1(zm, xm, ym, hk);
-    corr_combine<PATH>(q, c, fc, fi, gc, gj, hc, hk, xm, ym, zm, xp, yp, zp, P, out);
+    if (PATH == IMHD_PATH_B) fi[RHO] = xm[RHO];  // B-6
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        dF[v] = fc[v] - fi[v];
+        xsum[v] = PATH == IMHD_PATH_B ? xp[v] + xm[v] : 0.0f;
+    }
+    hflux_km1<float>(zm, xm[BX], ym[BY], ym[MY], hk);
+    corr_combine<PATH, float>(q, c, dF, gc, gj, hc, hk, xsum, ym, yp, zm, zp, P, out);
 }
 
 // Path B, k = 0 face (BoundaryConditions, kernels_fluidbcs.cu:52-116): corrector with INDEXED fluxes of
@@ -558,22 +561,23 @@ __global__ void __launch_bounds__(TI * 32, 1) k_fused_step_tma(const FusedArgs A
 }
 
 // -----------------------------------------------------------------------------------------------
-// The fused z-marching kernel, register-tiled rows (the hot path).  Same march, same TMA staging and
-// the same device functions as k_fused_step_tma, but every thread owns R consecutive rows (i) of one
-// column j, so that
-//   - F(Q) and F'(Qint) of a cell are evaluated once and reused as the i+1 / i-1 neighbour flux of the
-//     next row of the same thread (registers, no exchange),
-//   - the primitives of Q(k+1) are carried in the register queue from the iteration that evaluated
-//     H(Q(k+1)) instead of being re-derived,
-//   - only the first and the last row of a thread go through the Qint exchange array, and the x
-//     neighbours of the Laplacians inside the thread come from registers,
-//   - addressing, predicates, loop control and the barrier are paid once per R cells.
-// The thread tile is TI*R rows x 32 lanes: 8 warps x 2 rows give the 16x32 tile of the one-row kernel
-// with half the threads (255 registers each, no spills); 12 warps x 2 rows a 24x32 tile (22x30 outputs).
+// The fused z-marching kernel, register-tiled (the hot path).  Same march, same TMA staging and the same device
+// functions as k_fused_step_tma, but every thread owns TWO consecutive rows (i, i+1) of one column j, held as
+// float2 (.x = first row, .y = second row), so that
+//   - F(Q) and F'(Qint) of the first row are the i-1 neighbour flux of the second and the second row's flux is the
+//     first row's i+1 neighbour (registers, no exchange); the x neighbours of the Laplacians likewise,
+//   - the primitives of Q(k+1) are carried in the register queue from the iteration that evaluated H(Q(k+1)),
+//   - everything that is symmetric in the two rows and has at most two distinct register operands issues as ONE packed
+//     fp32x2 instruction (imhd_math.cuh),
+//   - addressing, predicates, loop control and the barrier are paid once per two cells.
+// The thread tile is 2*TI rows x 32 lanes: 8 warps give the 16x32 tile of the one-row kernel with half the threads
+// (<= 255 registers, no spills).  The march is ONE rolled copy of the plane body -- it has to fit the instruction
+// cache: with 8 warps per SM nobody hides a fetch miss (measured: 3x unrolled 29.9, rolled 31.6 GLUPS) -- so the
+// register queue rotates by moves.
 // -----------------------------------------------------------------------------------------------
-template <int PATH, int TI, int R>
-struct RowsGeo {
-    static constexpr int NR = TI * R;                                   // rows of the thread tile
+template <int PATH, int TI>
+struct PairGeo {
+    static constexpr int NR = TI * 2;                                   // rows of the thread tile
     static constexpr int TR = NR + 2;                                   // tile rows (one ring row either side)
     static constexpr int WI = PATH == IMHD_PATH_A ? NR - 1 : NR - 2;    // output rows per tile
     static constexpr int WJ = PATH == IMHD_PATH_A ? 31 : 30;            // output lanes per tile
@@ -583,13 +587,12 @@ struct RowsGeo {
     static constexpr size_t SMEM = 3 * STAGE_BYTES + 2 * XBUF * 4 + 64;
 };
 
-template <int R>
-struct RowsThread {  // per-thread constants
+struct PairThread {  // per-thread constants
     unsigned rows;          // per row rr: bit rr = bottom, 8+rr = interior i, 16+rr = corrector-updated row, 24+rr = owner row
     unsigned lanes;         // bit 0 = right, 1 = interior j, 2 = corrector-updated column, 3 = owner column
-    int own;                // tile offset of the cell of row 0
+    int own;                // tile offset of the cell of the first row
     int xs, xsm, xsp;       // exchange slots: own, thread row above, thread row below
-    int i0, jc;             // row of rr = 0; column clamped into the domain
+    int i0, jc;             // first row; column clamped into the domain
     __device__ __forceinline__ bool bottom(int rr) const { return (rows >> rr) & 1u; }
     __device__ __forceinline__ bool interior_i(int rr) const { return (rows >> (8 + rr)) & 1u; }
     __device__ __forceinline__ bool upd_i(int rr) const { return (rows >> (16 + rr)) & 1u; }
@@ -600,95 +603,100 @@ struct RowsThread {  // per-thread constants
     __device__ __forceinline__ bool owner_j() const { return lanes & 8u; }
 };
 
-// One plane of the march for the R rows of a thread: predictor plane k+1, corrector plane k.  Straight-line on
+// One plane of the march for the two rows of a thread: predictor plane k+1, corrector plane k.  Straight-line on
 // purpose: with 8 warps per SM every taken branch is an instruction-fetch bubble nobody hides, so the tile's ring
 // rows and the warm-up planes run the corrector too and only their STORES are predicated off (`store_ok`).
-template <int PATH, int TI, int R>
-__device__ __forceinline__ void rows_plane(const FusedArgs& A, const RowsThread<R>& T, bool hi, bool store_ok, const float* tq1,
-                                           const float* tq2, const float* xq, const float (&q0)[R][8],
-                                           const float (&q1)[R][8], float (&qn)[R][8], const float (&h1)[R][8],
-                                           float (&hn)[R][8], const Prim (&p1)[R], Prim (&pn)[R], const float (&qim)[R][8],
-                                           const float (&qic)[R][8], float (&qip)[R][8], float* outp) {
-    using G = RowsGeo<PATH, TI, R>;
+template <int PATH, int TI>
+__device__ __forceinline__ void pair_plane(const FusedArgs& A, const PairThread& T, bool hi, bool store_ok, const float* tq1,
+                                           const float* tq2, const float* xq, const float2 (&q0)[8], const float2 (&q1)[8],
+                                           float2 (&qn)[8], const float2 (&h1)[8], float2 (&hn)[8], const PrimT<float2>& p1,
+                                           PrimT<float2>& pn, const float2 (&qim)[8], const float2 (&qic)[8],
+                                           float2 (&qip)[8], float* outp) {
+    using G = PairGeo<PATH, TI>;
     const Params& P = A.P;
     constexpr int VS = G::TR * kTC;   // variable stride inside a tile
     constexpr int XV = TI * 32;       // variable stride inside an exchange buffer
+    const FlagT<float2> right = {T.right(), T.right()};
 #pragma unroll
-    for (int rr = 0; rr < R; ++rr) {
-#pragma unroll
-        for (int v = 0; v < 8; ++v) qn[rr][v] = tq2[v * VS + T.own + rr * kTC];
-        pn[rr] = make_prim(qn[rr]);
-        flux_idx<DIR_Z>(qn[rr], pn[rr], hn[rr]);
-    }
+    for (int v = 0; v < 8; ++v) qn[v] = make_float2(tq2[v * VS + T.own], tq2[v * VS + T.own + kTC]);
+    pn = make_prim(qn);
+    flux_idx<DIR_Z>(qn, pn, hn);
     // ---- predictor plane k+1 ---------------------------------------------------------------------------
     {
-        float xlast[8], xfirst[8], fa[8], fb[8];
+        float xlast[8], xfirst[8], fl[8];
+        float2 yp[8], ym[8], f[8], g[8], gy[8], dF[8], xsum[8];
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
-            xlast[v] = tq1[v * VS + T.own + R * kTC];                       // Q(k+1) one row below the thread's rows
-            if (PATH == IMHD_PATH_B) xfirst[v] = tq1[v * VS + T.own - kTC];  // ... and one row above
-        }
-        flux_idx<DIR_X>(q1[0], p1[0], fa);
-#pragma unroll
-        for (int rr = 0; rr < R; ++rr) {
-            const float* xp = rr < R - 1 ? q1[rr + 1 < R ? rr + 1 : rr] : xlast;
-            const float* xm = rr > 0 ? q1[rr > 0 ? rr - 1 : 0] : xfirst;
-            if (rr < R - 1) flux_idx<DIR_X>(q1[rr + 1 < R ? rr + 1 : rr], p1[rr + 1 < R ? rr + 1 : rr], fb);
-            else            flux_idx<DIR_X>(xlast, make_prim(xlast), fb);
-            float g[8], gy[8], yp[8], ym[8];
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-                yp[v] = tq1[v * VS + T.own + rr * kTC + 1];
-                if (PATH == IMHD_PATH_B) ym[v] = tq1[v * VS + T.own + rr * kTC - 1];
+            xlast[v] = tq1[v * VS + T.own + 2 * kTC];                       // Q(k+1) one row below the thread's rows
+            yp[v] = make_float2(tq1[v * VS + T.own + 1], tq1[v * VS + T.own + kTC + 1]);
+            if (PATH == IMHD_PATH_B) {
+                xfirst[v] = tq1[v * VS + T.own - kTC];                      // ... and one row above
+                ym[v] = make_float2(tq1[v * VS + T.own - 1], tq1[v * VS + T.own + kTC - 1]);
             }
-            flux_idx<DIR_Y>(q1[rr], p1[rr], g);
-            flux_idx<DIR_Y>(yp, make_prim(yp), gy);
-            qint_combine<PATH>(q1[rr], fa, fb, g, gy, h1[rr], hn[rr], xm, xp, ym, yp, q0[rr], qn[rr], T.bottom(rr),
-                               T.right(), false, T.interior_i(rr) && T.interior_j(), P, qip[rr]);
-#pragma unroll
-            for (int v = 0; v < 8; ++v) fa[v] = fb[v];
         }
+        flux_idx<DIR_X>(q1, p1, f);
+        flux_idx<DIR_X>(xlast, make_prim(xlast), fl);
+        flux_idx<DIR_Y>(q1, p1, g);
+        flux_idx<DIR_Y>(yp, make_prim(yp), gy);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            dF[v].x = T.bottom(0) ? -f[v].x : f[v].y - f[v].x;   // the second row's flux is the first row's i+1 neighbour
+            dF[v].y = T.bottom(1) ? -f[v].y : fl[v] - f[v].y;
+            if (PATH == IMHD_PATH_B) xsum[v] = make_float2(q1[v].y + xfirst[v], xlast[v] + q1[v].x);
+        }
+        qint_combine<PATH, float2>(q1, dF, g, gy, h1, hn, xsum, ym, yp, q0, qn, {T.bottom(0), T.bottom(1)}, right,
+                                   {T.interior_i(0) && T.interior_j(), T.interior_i(1) && T.interior_j()}, P, qip);
     }
     if (__builtin_expect(hi, 0)) {  // the plane above the slab comes from the neighbour (or is the periodic image): once per slab
+        float a[8], b[8];
+        ldg8(A.qhi, (long long)min(T.i0, P.Nx - 1) * P.Ny + T.jc, P.plane, a);
+        ldg8(A.qhi, (long long)min(T.i0 + 1, P.Nx - 1) * P.Ny + T.jc, P.plane, b);
 #pragma unroll
-        for (int rr = 0; rr < R; ++rr) ldg8(A.qhi, (long long)min(T.i0 + rr, P.Nx - 1) * P.Ny + T.jc, P.plane, qip[rr]);
+        for (int v = 0; v < 8; ++v) qip[v] = make_float2(a[v], b[v]);
     }
     // ---- corrector plane k -----------------------------------------------------------------------------
     {
-        float xfirst[8], xlast[8], fa[8];
+        float xfirst[8], xlast[8], ff[8];
+        float2 fc[8], gc[8], hc[8], gj[8], hk[8], ym[8], yp[8], dF[8], xsum[8], out[8];
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
-            xfirst[v] = xq[(8 + v) * XV + T.xsm];                          // Qint(k), last row of the thread row above
+            xfirst[v] = xq[(8 + v) * XV + T.xsm];                          // Qint(k), second row of the thread row above
             if (PATH == IMHD_PATH_B) xlast[v] = xq[v * XV + T.xsp];        // ... first row of the thread row below
         }
-        flux_loc<DIR_X>(xfirst, make_prim(xfirst), fa);
+        const PrimT<float2> sc = make_prim(qic);
+        flux_loc<DIR_X>(qic, sc, fc);
+        flux_loc<DIR_Y>(qic, sc, gc);
+        flux_loc<DIR_Z>(qic, sc, hc);
+        flux_loc<DIR_X>(xfirst, make_prim(xfirst), ff);
 #pragma unroll
-        for (int rr = 0; rr < R; ++rr) {
-            const float* c = qic[rr];
-            const Prim sc = make_prim(c);
-            const float* xm = rr > 0 ? qic[rr > 0 ? rr - 1 : 0] : xfirst;
-            const float* xp = rr < R - 1 ? qic[rr + 1 < R ? rr + 1 : rr] : xlast;
-            float fc[8], gc[8], hc[8], gj[8], hk[8], ym[8], yp[8], out[8];
-            flux_loc<DIR_X>(c, sc, fc);
-            flux_loc<DIR_Y>(c, sc, gc);
-            flux_loc<DIR_Z>(c, sc, hc);
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-                ym[v] = __shfl_up_sync(0xffffffffu, c[v], 1);
-                if (PATH == IMHD_PATH_B) yp[v] = __shfl_down_sync(0xffffffffu, c[v], 1);
-                gj[v] = v == BY ? 0.0f : __shfl_up_sync(0xffffffffu, gc[v], 1);
-            }
-            hflux_km1(qim[rr], xm, ym, hk);
-            corr_combine<PATH>(q0[rr], c, fc, fa, gc, gj, hc, hk, xm, ym, qim[rr], xp, yp, qip[rr], P, out);
-            if (store_ok && T.owner_i(rr) && T.owner_j()) {
-                char* o = reinterpret_cast<char*>(outp + (long long)rr * P.Ny);
-                const bool upd = T.upd_i(rr) && T.upd_j();
+        for (int v = 0; v < 8; ++v) {
+            ym[v] = make_float2(__shfl_up_sync(0xffffffffu, qic[v].x, 1), __shfl_up_sync(0xffffffffu, qic[v].y, 1));
+            if (PATH == IMHD_PATH_B)
+                yp[v] = make_float2(__shfl_down_sync(0xffffffffu, qic[v].x, 1), __shfl_down_sync(0xffffffffu, qic[v].y, 1));
+            gj[v] = v == BY ? make_float2(0.0f, 0.0f)
+                            : make_float2(__shfl_up_sync(0xffffffffu, gc[v].x, 1), __shfl_up_sync(0xffffffffu, gc[v].y, 1));
+            // F'(Qint(i-1)): the thread row above for the first row, the first row's own flux for the second (B-6: rho)
+            const float fa = (PATH == IMHD_PATH_B && v == RHO) ? xfirst[RHO] : ff[v];
+            const float fb = (PATH == IMHD_PATH_B && v == RHO) ? qic[RHO].x : fc[v].x;
+            dF[v] = make_float2(fc[v].x - fa, fc[v].y - fb);
+            if (PATH == IMHD_PATH_B) xsum[v] = make_float2(qic[v].y + xfirst[v], xlast[v] + qic[v].x);
+        }
+        hflux_km1<float2>(qim, make_float2(xfirst[BX], qic[BX].x), ym[BY], ym[MY], hk);
+        corr_combine<PATH, float2>(q0, qic, dF, gc, gj, hc, hk, xsum, ym, yp, qim, qip, P, out);
+        if (store_ok && T.owner_j()) {
+            const bool ua = T.upd_i(0) && T.upd_j(), ub = T.upd_i(1) && T.upd_j();
+            if (T.owner_i(0)) {
+                char* o = reinterpret_cast<char*>(outp);
 #pragma unroll
                 for (int v = 0; v < 8; ++v)  // untouched cells are carried over
-                    *reinterpret_cast<float*>(o + (unsigned long long)A.vs32 * (unsigned)(4 * v)) = upd ? out[v] : q0[rr][v];
+                    *reinterpret_cast<float*>(o + (unsigned long long)A.vs32 * (unsigned)(4 * v)) = ua ? out[v].x : q0[v].x;
             }
+            if (T.owner_i(1)) {
+                char* o = reinterpret_cast<char*>(outp + P.Ny);
 #pragma unroll
-            for (int v = 0; v < 8; ++v) fa[v] = fc[v];
+                for (int v = 0; v < 8; ++v)
+                    *reinterpret_cast<float*>(o + (unsigned long long)A.vs32 * (unsigned)(4 * v)) = ub ? out[v].y : q0[v].y;
+            }
         }
     }
 }
@@ -697,9 +705,9 @@ __device__ __forceinline__ void rows_plane(const FusedArgs& A, const RowsThread<
 __device__ __forceinline__ void keep(int& x) { asm volatile("" : "+r"(x)); }
 __device__ __forceinline__ void keep(unsigned& x) { asm volatile("" : "+r"(x)); }
 
-template <int PATH, int TI, int R, bool ROLLED>
-__global__ void __launch_bounds__(TI * 32, 1) k_fused_rows(const FusedArgs A, const __grid_constant__ CUtensorMap tmap) {
-    using G = RowsGeo<PATH, TI, R>;
+template <int PATH, int TI>
+__global__ void __launch_bounds__(TI * 32, 1) k_fused_pair(const FusedArgs A, const __grid_constant__ CUtensorMap tmap) {
+    using G = PairGeo<PATH, TI>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);                       // [3][8][TR][kTC]
     float* xch = tiles + 3 * G::STAGE_FLOATS;                                 // [2][first,last][8][TI][32]  Qint exchange
@@ -709,13 +717,13 @@ __global__ void __launch_bounds__(TI * 32, 1) k_fused_rows(const FusedArgs A, co
     const int lane = threadIdx.x, ti = threadIdx.y;
     const int bi = blockIdx.y, bj = blockIdx.x;
     const int ib = bi * G::WI, jb = bj * G::WJ;
-    const int t0 = ti * R, i0 = ib + t0, j = jb + lane;
+    const int t0 = ti * 2, i0 = ib + t0, j = jb + lane;
     const int oi_lo = bi == 0 ? 0 : ib + 1, oi_hi = bi == A.ntile_i - 1 ? P.Nx : ib + G::WI + 1;
     const int oj_lo = bj == 0 ? 0 : jb + 1, oj_hi = bj == A.ntile_j - 1 ? P.Ny : jb + G::WJ + 1;
-    RowsThread<R> T;
+    PairThread T;
     T.rows = 0;
 #pragma unroll
-    for (int rr = 0; rr < R; ++rr) {
+    for (int rr = 0; rr < 2; ++rr) {
         const int i = i0 + rr, t = t0 + rr;
         const bool corr_row = t >= 1 && (PATH == IMHD_PATH_A || t <= G::NR - 2);  // rows with valid Qint neighbours
         if (i == P.Nx - 1) T.rows |= 1u << rr;
@@ -757,97 +765,58 @@ __global__ void __launch_bounds__(TI * 32, 1) k_fused_rows(const FusedArgs A, co
     if (producer)
         for (int s = 0; s < 3; ++s) issue(ks + s, s);
 
-    float qa[R][8], qb[R][8], qc[R][8], ha[R][8], hb[R][8], hc[R][8], ia[R][8], ib_[R][8], ic[R][8];
-    Prim pa[R], pb[R], pc[R];
+    float2 qa[8], qb[8], qc[8], hb[8], hc[8], ia[8], ib_[8], ic[8];
+    PrimT<float2> pb, pc;
     constexpr int VS = G::TR * kTC;
     mbar_wait(&full[0], 0);
     mbar_wait(&full[1], 0);
 #pragma unroll
-    for (int rr = 0; rr < R; ++rr) {
+    for (int v = 0; v < 8; ++v) {
+        qa[v] = make_float2(tiles[v * VS + T.own], tiles[v * VS + T.own + kTC]);
+        qb[v] = make_float2(tiles[G::STAGE_FLOATS + v * VS + T.own], tiles[G::STAGE_FLOATS + v * VS + T.own + kTC]);
+        ia[v] = make_float2(1.0f, 1.0f);
+        ib_[v] = make_float2(1.0f, 1.0f);
+    }
+    pb = make_prim(qb);
+    flux_idx<DIR_Z>(qb, pb, hb);
+    if (first) {  // Qint(ka-1); rows beyond the domain read the last row (they never produce output)
+        float a[8], b[8];
+        ldg8(A.qlo, (long long)min(i0, P.Nx - 1) * P.Ny + T.jc, P.plane, a);
+        ldg8(A.qlo, (long long)min(i0 + 1, P.Nx - 1) * P.Ny + T.jc, P.plane, b);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) ib_[v] = make_float2(a[v], b[v]);
+    }
+
+    // output pointer of the first row at plane ks; stores are predicated off below plane ka
+    float* outp = A.Qout + (long long)(ks - A.kbase) * P.plane + (long long)i0 * P.Ny + T.jc;
+    int xsel = 0;        // exchange buffer of this plane (floats): alternates between 0 and XBUF
+    int s2 = 2;          // stage of plane k+2
+    uint32_t par = 0x3;  // bit s = parity of the next wait on stage s: stages 0,1 were waited once in the prologue
+#pragma unroll 1
+    for (int k = ks; k < kb; ++k) {
+        const int s1 = s2 == 0 ? 2 : s2 - 1, sfree = s1 == 0 ? 2 : s1 - 1;
+        float* xq = xch + xsel;
+        xsel ^= G::XBUF;
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
-            qa[rr][v] = tiles[v * VS + T.own + rr * kTC];
-            qb[rr][v] = tiles[G::STAGE_FLOATS + v * VS + T.own + rr * kTC];
-            ia[rr][v] = 1.0f;
-            ib_[rr][v] = 1.0f;
+            xq[v * TI * 32 + T.xs] = ib_[v].x;
+            xq[(8 + v) * TI * 32 + T.xs] = ib_[v].y;
         }
-        pb[rr] = make_prim(qb[rr]);
-        flux_idx<DIR_Z>(qb[rr], pb[rr], hb[rr]);
-        // Qint(ka-1); rows beyond the domain read the last row (they never produce output)
-        if (first) ldg8(A.qlo, (long long)min(i0 + rr, P.Nx - 1) * P.Ny + T.jc, P.plane, ib_[rr]);
-    }
-
-    // output pointer of row 0 at plane ks; stores are predicated off below plane ka
-    float* outp = A.Qout + (long long)(ks - A.kbase) * P.plane + (long long)i0 * P.Ny + T.jc;
-    int xsel = 0;  // exchange buffer of this plane (floats): alternates between 0 and XBUF
-    int k = ks;
-
-    if (ROLLED) {
-        // one copy of the plane body (fits the instruction cache); the register queue rotates by moves
-        int s2 = 2;         // stage of plane k+2, and the parity of its next mbarrier phase
-        uint32_t par = 0;   // bit s = parity of the next wait on stage s: stages 0,1 were waited once in the prologue
-        par = 0x3;
-#pragma unroll 1
-        for (; k < kb; ++k) {
-            const int s1 = s2 == 0 ? 2 : s2 - 1, sfree = s1 == 0 ? 2 : s1 - 1;
-            float* xq = xch + xsel;
-            xsel ^= G::XBUF;
+        mbar_wait(&full[s2], (par >> s2) & 1u);
+        par ^= 1u << s2;
+        __syncthreads();
+        if (producer && k + 3 <= klast) issue(k + 3, sfree);
+        pair_plane<PATH, TI>(A, T, k + 1 == A.hi_plane, k >= ka, tiles + s1 * G::STAGE_FLOATS, tiles + s2 * G::STAGE_FLOATS, xq,
+                             qa, qb, qc, hb, hc, pb, pc, ia, ib_, ic, outp);
+        outp += P.plane;
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
-                xq[v * TI * 32 + T.xs] = ib_[0][v];
-                xq[(8 + v) * TI * 32 + T.xs] = ib_[R - 1][v];
-            }
-            mbar_wait(&full[s2], (par >> s2) & 1u);
-            par ^= 1u << s2;
-            __syncthreads();
-            if (producer && k + 3 <= klast) issue(k + 3, sfree);
-            rows_plane<PATH, TI, R>(A, T, k + 1 == A.hi_plane, k >= ka, tiles + s1 * G::STAGE_FLOATS, tiles + s2 * G::STAGE_FLOATS, xq,
-                                    qa, qb, qc, hb, hc, pb, pc, ia, ib_, ic, outp);
-            outp += P.plane;
-#pragma unroll
-            for (int rr = 0; rr < R; ++rr) {
-#pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    qa[rr][v] = qb[rr][v]; qb[rr][v] = qc[rr][v]; hb[rr][v] = hc[rr][v];
-                    ia[rr][v] = ib_[rr][v]; ib_[rr][v] = ic[rr][v];
-                }
-                pb[rr] = pc[rr];
-            }
-            s2 = s2 == 2 ? 0 : s2 + 1;
+        for (int v = 0; v < 8; ++v) {
+            qa[v] = qb[v]; qb[v] = qc[v]; hb[v] = hc[v];
+            ia[v] = ib_[v]; ib_[v] = ic[v];
         }
-        return;
+        pb = pc;
+        s2 = s2 == 2 ? 0 : s2 + 1;
     }
-
-    float* t0p = tiles;
-    float* t1p = tiles + G::STAGE_FLOATS;
-    float* t2p = tiles + 2 * G::STAGE_FLOATS;
-    // one step of the march; roles (Q(k),Q(k+1),Q(k+2)) and their H / primitives, (Qint(k-1),Qint(k),Qint(k+1)) and the
-    // three tile stages rotate by renaming (period 3); the exchange buffer alternates at run time
-#define IMHD_ROWS_MARCH(Q0, Q1, QN, H1, HN, P1, PN, IM, IC, IP, TQ1, TQ2, SFREE, S2)                                   \
-    if (k < kb) {                                                                                                     \
-        float* xq = xch + xsel;                                                                                       \
-        xsel ^= G::XBUF;                                                                                              \
-        _Pragma("unroll") for (int v = 0; v < 8; ++v) {                                                               \
-            xq[v * TI * 32 + T.xs] = IC[0][v];                                                                        \
-            xq[(8 + v) * TI * 32 + T.xs] = IC[R - 1][v];                                                              \
-        }                                                                                                             \
-        mbar_wait(&full[S2], par##S2);                                                                                \
-        par##S2 ^= 1;                                                                                                 \
-        __syncthreads();                                                                                              \
-        if (producer && k + 3 <= klast) issue(k + 3, SFREE);                                                          \
-        rows_plane<PATH, TI, R>(A, T, k + 1 == A.hi_plane, k >= ka, TQ1, TQ2, xq, Q0, Q1, QN, H1, HN, P1, PN, IM, IC, IP, outp); \
-        outp += P.plane;                                                                                              \
-        ++k;                                                                                                          \
-    }
-
-    // parity of the NEXT wait on each stage: stages 0,1 were waited once in the prologue
-    uint32_t par0 = 1, par1 = 1, par2 = 0;
-    while (k < kb) {
-        IMHD_ROWS_MARCH(qa, qb, qc, hb, hc, pb, pc, ia, ib_, ic, t1p, t2p, 0, 2)
-        IMHD_ROWS_MARCH(qb, qc, qa, hc, ha, pc, pa, ib_, ic, ia, t2p, t0p, 1, 0)
-        IMHD_ROWS_MARCH(qc, qa, qb, ha, hb, pa, pb, ic, ia, ib_, t0p, t1p, 2, 1)
-    }
-#undef IMHD_ROWS_MARCH
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -1234,11 +1203,11 @@ struct OneRowLaunch {
     static constexpr int THREAD_ROWS = TI;
     static auto kernel() { return k_fused_step_tma<PATH, TI>; }
 };
-template <int PATH, int TI, int R, bool ROLLED>
-struct RowsLaunch {
-    using G = RowsGeo<PATH, TI, R>;
+template <int PATH, int TI>
+struct PairLaunch {
+    using G = PairGeo<PATH, TI>;
     static constexpr int THREAD_ROWS = TI;
-    static auto kernel() { return k_fused_rows<PATH, TI, R, ROLLED>; }
+    static auto kernel() { return k_fused_pair<PATH, TI>; }
 };
 
 template <int PATH, class L>
@@ -1300,11 +1269,8 @@ static int launch_fused(FusedArgs& A, int nplanes_array, cudaStream_t st) {
         case 1:
             if (make_tile_map(&tmap, A, nplanes_array, TmaGeo<PATH, 16>::TR)) return launch_tma<PATH, OneRowLaunch<PATH, 16>>(A, tmap, st);
             break;
-        case 2:
-            if (make_tile_map(&tmap, A, nplanes_array, RowsGeo<PATH, 8, 2>::TR)) return launch_tma<PATH, RowsLaunch<PATH, 8, 2, true>>(A, tmap, st);
-            break;
         default:
-            if (make_tile_map(&tmap, A, nplanes_array, RowsGeo<PATH, 8, 2>::TR)) return launch_tma<PATH, RowsLaunch<PATH, 8, 2, false>>(A, tmap, st);
+            if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, PairLaunch<PATH, 8>>(A, tmap, st);
             break;
     }
     constexpr int TI = 16;

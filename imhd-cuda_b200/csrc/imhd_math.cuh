@@ -177,74 +177,125 @@ __device__ __forceinline__ void flux_local(const float U[8], float p, float Bsq,
 // FAST recipe, flux tensors from once-per-state primitives.  The two families differ only in the
 // induction and energy fluxes; momentum fluxes and the aliases F(my)=G(mx), F(mz)=H(mx),
 // G(mz)=H(my) (kernels_od_fluxes.cu:152-183) are shared.  ~19 ops per state + ~13 per direction.
+//
+// Generic over the value type V:
+//   V = float    one cell
+//   V = float2   the two rows a thread of the register-tiled kernel owns (.x = first row, .y = second).  Operations with
+//                at most two distinct register operands (the third a broadcast scalar, an immediate or a repeated
+//                operand) are ONE packed fp32x2 instruction (FFMA2 / FMUL2 / FADD2): measured on B200
+//                (tools/probe/packed_const_probe.cu) such an instruction holds the fp32 pipe for two cycles but the
+//                issue port for one, so the slot it frees goes to the loads, shuffles and moves of the march.  A
+//                multiply-add of three distinct register pairs would run at half rate as FFMA2 (three pairs, four
+//                banks) and stays two scalar FFMA (`vfma3`).
+// Each half of a packed instruction rounds exactly like the scalar instruction and both instantiations are the same
+// text, so they give the same bits.
 // ------------------------------------------------------------------------------------------
-struct Prim {
-    float ux, uy, uz;   // m / rho
-    float Bsq, p, ptot, Bdotu;
-};
+__device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float vfma3(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float vfmac(float k, float a, float c) { return fmaf(k, a, c); }   // constant multiplier
+__device__ __forceinline__ float vmul(float a, float b) { return a * b; }
+__device__ __forceinline__ float vmulc(float k, float a) { return k * a; }
+__device__ __forceinline__ float vadd(float a, float b) { return a + b; }
+__device__ __forceinline__ float vsub(float a, float b) { return a - b; }
+__device__ __forceinline__ float vneg(float a) { return -a; }
+__device__ __forceinline__ float vrcp(float a) { return fast_rcp(a); }
+__device__ __forceinline__ float2 vneg(float2 a) { return make_float2(-a.x, -a.y); }  // folds into operand modifiers
+__device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 vfma3(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 vfmac(float k, float2 a, float2 c) { return __ffma2_rn(make_float2(k, k), a, c); }
+__device__ __forceinline__ float2 vmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 vmulc(float k, float2 a) { return __fmul2_rn(make_float2(k, k), a); }
+__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 vsub(float2 a, float2 b) { return __fadd2_rn(a, vneg(b)); }
+__device__ __forceinline__ float2 vrcp(float2 a) {
+    float2 r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(a.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(a.y));
+    return vfma(r, vfma(vneg(a), r, make_float2(1.0f, 1.0f)), r);
+}
+template <class V> __device__ __forceinline__ V vset(float s);
+template <> __device__ __forceinline__ float vset<float>(float s) { return s; }
+template <> __device__ __forceinline__ float2 vset<float2>(float s) { return make_float2(s, s); }
 
-__device__ __forceinline__ Prim make_prim(const float U[8]) {
-    Prim s;
-    const float inv = fast_rcp(U[RHO]);
-    s.ux = U[MX] * inv; s.uy = U[MY] * inv; s.uz = U[MZ] * inv;
-    s.Bsq = fmaf(U[BZ], U[BZ], fmaf(U[BY], U[BY], U[BX] * U[BX]));
-    const float ke = fmaf(s.uz, U[MZ], fmaf(s.uy, U[MY], s.ux * U[MX]));   // (m.m)/rho, no 1/2 (B-1)
-    s.p = kGm1f * fmaf(-0.5f, s.Bsq, U[EN] - ke);
-    s.ptot = fmaf(0.5f, s.Bsq, s.p);
-    s.Bdotu = fmaf(s.uz, U[BZ], fmaf(s.uy, U[BY], s.ux * U[BX]));
+// per-half predicates of a value
+template <class V> struct FlagT;
+template <> struct FlagT<float> { bool x; };
+template <> struct FlagT<float2> { bool x, y; };
+__device__ __forceinline__ float vsel(FlagT<float> f, float a, float b) { return f.x ? a : b; }
+__device__ __forceinline__ float2 vsel(FlagT<float2> f, float2 a, float2 b) { return make_float2(f.x ? a.x : b.x, f.y ? a.y : b.y); }
+__device__ __forceinline__ FlagT<float> fand(FlagT<float> a, FlagT<float> b) { return {a.x && b.x}; }
+__device__ __forceinline__ FlagT<float2> fand(FlagT<float2> a, FlagT<float2> b) { return {a.x && b.x, a.y && b.y}; }
+
+template <class V>
+struct PrimT {
+    V ux, uy, uz;   // m / rho
+    V Bsq, p, ptot, Bdotu;
+};
+typedef PrimT<float> Prim;
+
+template <class V>
+__device__ __forceinline__ PrimT<V> make_prim(const V U[8]) {
+    PrimT<V> s;
+    const V inv = vrcp(U[RHO]);
+    s.ux = vmul(U[MX], inv); s.uy = vmul(U[MY], inv); s.uz = vmul(U[MZ], inv);
+    s.Bsq = vfma(U[BZ], U[BZ], vfma(U[BY], U[BY], vmul(U[BX], U[BX])));
+    const V ke = vfma3(s.uz, U[MZ], vfma3(s.uy, U[MY], vmul(s.ux, U[MX])));   // (m.m)/rho, no 1/2 (B-1)
+    s.p = vmulc(kGm1f, vfmac(-0.5f, s.Bsq, vsub(U[EN], ke)));
+    s.ptot = vfmac(0.5f, s.Bsq, s.p);
+    s.Bdotu = vfma3(s.uz, U[BZ], vfma3(s.uy, U[BY], vmul(s.ux, U[BX])));
     return s;
 }
 
 // momentum part of the d-direction flux, common to both families
-template <int DIR>
-__device__ __forceinline__ void flux_mom(const float U[8], const Prim& s, float f[8]) {
-    const float ud = DIR == DIR_X ? s.ux : (DIR == DIR_Y ? s.uy : s.uz);
-    const float bd = U[BX + DIR];
+template <int DIR, class V>
+__device__ __forceinline__ void flux_mom(const V U[8], const PrimT<V>& s, V f[8]) {
+    const V ud = DIR == DIR_X ? s.ux : (DIR == DIR_Y ? s.uy : s.uz);
+    const V bd = U[BX + DIR];
     f[RHO] = U[MX + DIR];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         if (c == DIR) {
-            f[MX + c] = fmaf(ud, U[MX + c], fmaf(-bd, bd, s.ptot));
+            f[MX + c] = vfma3(ud, U[MX + c], vfma(vneg(bd), bd, s.ptot));
         } else {
             // (m_lo/rho) * m_hi - B_lo*B_hi with lo < hi: one expression for both aliases
             const int lo = c < DIR ? c : DIR, hi = c < DIR ? DIR : c;
-            const float ulo = lo == 0 ? s.ux : s.uy;
-            f[MX + c] = fmaf(ulo, U[MX + hi], -(U[BX + lo] * U[BX + hi]));
+            const V ulo = lo == 0 ? s.ux : s.uy;
+            f[MX + c] = vfma3(ulo, U[MX + hi], vneg(vmul(U[BX + lo], U[BX + hi])));
         }
     }
-    f[BX + DIR] = 0.0f;
+    f[BX + DIR] = vset<V>(0.0f);
 }
 
 // INDEXED family (predictor): induction with the undivided term (B-2), energy without parentheses (B-3)
-template <int DIR>
-__device__ __forceinline__ void flux_idx(const float U[8], const Prim& s, float f[8]) {
+template <int DIR, class V>
+__device__ __forceinline__ void flux_idx(const V U[8], const PrimT<V>& s, V f[8]) {
     flux_mom<DIR>(U, s, f);
-    const float ud = DIR == DIR_X ? s.ux : (DIR == DIR_Y ? s.uy : s.uz);
-    const float md = U[MX + DIR], bd = U[BX + DIR];
+    const V ud = DIR == DIR_X ? s.ux : (DIR == DIR_Y ? s.uy : s.uz);
+    const V md = U[MX + DIR], bd = U[BX + DIR];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         if (c == DIR) continue;
-        const float uc = c == 0 ? s.ux : (c == 1 ? s.uy : s.uz);
+        const V uc = c == 0 ? s.ux : (c == 1 ? s.uy : s.uz);
         // c < DIR: (m_c/rho) B_d - B_c m_d ;  c > DIR: -( (m_d/rho) B_c - B_d m_c )
-        if (c < DIR) f[BX + c] = fmaf(uc, bd, -(U[BX + c] * md));
-        else         f[BX + c] = fmaf(bd, U[MX + c], -(ud * U[BX + c]));
+        if (c < DIR) f[BX + c] = vfma3(uc, bd, vneg(vmul(U[BX + c], md)));
+        else         f[BX + c] = vfma3(bd, U[MX + c], vneg(vmul(ud, U[BX + c])));
     }
-    f[EN] = fmaf(-s.Bdotu, bd, fmaf(s.Bsq, ud, U[EN] + s.p));
+    f[EN] = vfma3(vneg(s.Bdotu), bd, vfma3(s.Bsq, ud, vadd(U[EN], s.p)));
 }
 
 // LOCAL family (corrector): (m_c/rho) B_d - (m_d/rho) B_c ; (e + p + Bsq/2)(m_d/rho) - Bdotu B_d
-template <int DIR>
-__device__ __forceinline__ void flux_loc(const float U[8], const Prim& s, float f[8]) {
+template <int DIR, class V>
+__device__ __forceinline__ void flux_loc(const V U[8], const PrimT<V>& s, V f[8]) {
     flux_mom<DIR>(U, s, f);
-    const float ud = DIR == DIR_X ? s.ux : (DIR == DIR_Y ? s.uy : s.uz);
-    const float bd = U[BX + DIR];
+    const V ud = DIR == DIR_X ? s.ux : (DIR == DIR_Y ? s.uy : s.uz);
+    const V bd = U[BX + DIR];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         if (c == DIR) continue;
-        const float uc = c == 0 ? s.ux : (c == 1 ? s.uy : s.uz);
-        f[BX + c] = fmaf(uc, bd, -(ud * U[BX + c]));
+        const V uc = c == 0 ? s.ux : (c == 1 ? s.uy : s.uz);
+        f[BX + c] = vfma3(uc, bd, vneg(vmul(ud, U[BX + c])));
     }
-    f[EN] = fmaf(U[EN] + s.ptot, ud, -(s.Bdotu * bd));
+    f[EN] = vfma3(vadd(U[EN], s.ptot), ud, vneg(vmul(s.Bdotu, bd)));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -258,12 +309,13 @@ struct DiffCoef {
     float dtD;             // fast: dt * D
 };
 
-// fast: q + dt*D*lap folded into one chain: r + dtD * (cx (xp+xm) + cy (yp+ym) + cz (zp+zm) + c0 q).
+// fast: q + dt*D*lap folded into one chain: r + dtD * (cx (xp+xm) + cy (yp+ym) + cz (zp+zm) + c0 q), from the three
+// neighbour sums (the caller forms them: inside a register-tiled thread the x sum mixes its own rows).
 // The cancellation error of this form is ~1e-7 * (2/dx^2) * dt*D * |q| << ulp(q) for every grid of interest.
-__device__ __forceinline__ float add_diffusion(float r, float q, float xp, float yp, float zp, float xm, float ym, float zm,
-                                               const DiffCoef& c) {
-    const float lap = fmaf(c.cxf, xp + xm, fmaf(c.cyf, yp + ym, fmaf(c.czf, zp + zm, c.c0f * q)));
-    return fmaf(c.dtD, lap, r);
+template <class V>
+__device__ __forceinline__ V add_diffusion(V r, V q, V xsum, V ysum, V zsum, const DiffCoef& c) {
+    const V lap = vfmac(c.cxf, xsum, vfmac(c.cyf, ysum, vfmac(c.czf, zsum, vmulc(c.c0f, q))));
+    return vfmac(c.dtD, lap, r);
 }
 
 template <bool EXACT>
