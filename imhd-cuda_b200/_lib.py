@@ -88,6 +88,14 @@ SIGNATURES = {
     "imhd_ctx_flush_output": (_i, [_p]),
     "imhd_ctx_write_grid": (_i, [_p, C.c_char_p]),
     "imhd_run_host": (_i, [_p, _p, _p, _i, _f, _f, _f, _f, _f, _i]),
+    "imhd_create_multi": (_p, _dims + [_i, C.POINTER(_i)]),
+    "imhd_create_slab": (_p, _dims + [_i, _i, _i, _p]),
+    "imhd_nccl_unique_id": (_i, [_p, _i]),
+    "imhd_ctx_num_slabs": (_i, [_p]),
+    "imhd_ctx_slab_extent": (_i, [_p, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "imhd_ctx_set_state_local": (_i, [_p, _i, _p]),
+    "imhd_ctx_get_state_local": (_i, [_p, _i, _p]),
+    "imhd_set_edge_planes": (None, [_i]),
 }
 
 

@@ -40,7 +40,10 @@ void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxe
 
 using namespace imhd;
 
+#include "imhd_engine.h"
+
 struct imhd_ctx {
+    imhd::Engine* eng;         // multi-GPU contexts (imhd_create_multi / imhd_create_slab): the z-slab engine owns everything
     int Nx, Ny, Nz, device;
     size_t cells;
     float* buf[2];  // ping-pong state buffers; buf[cur] holds Q^n.  buf[1-cur] is the reference's `intvars`
@@ -57,7 +60,8 @@ struct imhd_ctx {
     float* snap;             // device snapshot of the frame being written out
     float* pinned[2];        // pinned host staging, double buffered
     cudaStream_t copy_stream;
-    cudaEvent_t snap_done, copy_done[2];
+    cudaEvent_t snap_done, snap_free, copy_done[2];
+    bool snap_used;          // a D2H copy out of `snap` has been queued: the next snapshot waits for snap_free
     int next_slot;
     struct Job { int slot, frame, attrs; std::string path; };
     std::deque<Job>* jobs;
@@ -67,6 +71,7 @@ struct imhd_ctx {
     bool slot_busy[2];
     bool stop;
     int write_errors;
+    char write_error_text[256];  // the writer thread's last error (its set_error is thread-local)
 };
 
 extern "C" int imhd_abi_version(void) { return 1; }
@@ -103,8 +108,56 @@ extern "C" imhd_ctx* imhd_create(int Nx, int Ny, int Nz, int device) {
     return c;
 }
 
+static void free_writer_buffers(imhd_ctx* c);
+
+static imhd_ctx* wrap_engine(Engine* e, int Nx, int Ny, int Nz, int device) {
+    if (!e) return nullptr;
+    imhd_ctx* c = new (std::nothrow) imhd_ctx();
+    if (!c) { eng_destroy(e); set_error("out of host memory"); return nullptr; }
+    memset(c, 0, sizeof(*c));
+    c->eng = e; c->Nx = Nx; c->Ny = Ny; c->Nz = Nz; c->device = device;
+    c->cells = (size_t)Nx * Ny * Nz;
+    return c;
+}
+
+// The whole domain as n_gpus z-slabs driven from THIS process (one slab per device, ring neighbours over NVLink).
+// n_gpus == 1 is the plain single-GPU context.
+extern "C" imhd_ctx* imhd_create_multi(int Nx, int Ny, int Nz, int n_gpus, const int* devices) {
+    if (n_gpus < 1) { set_error("imhd_create_multi: n_gpus = %d", n_gpus); return nullptr; }
+    if (n_gpus == 1) return imhd_create(Nx, Ny, Nz, devices ? devices[0] : 0);
+    std::vector<int> ranks(n_gpus), devs(n_gpus);
+    for (int q = 0; q < n_gpus; ++q) { ranks[q] = q; devs[q] = devices ? devices[q] : q; }
+    return wrap_engine(eng_create(Nx, Ny, Nz, n_gpus, n_gpus, ranks.data(), devs.data(), nullptr), Nx, Ny, Nz, devs[0]);
+}
+
+// Slab `rank` of `world` in THIS process (one process per GPU); nccl_unique_id = the 128 bytes of imhd_nccl_unique_id
+// made by one process and handed to all of them.
+extern "C" imhd_ctx* imhd_create_slab(int Nx, int Ny, int Nz, int rank, int world, int device, const void* nccl_unique_id) {
+    if (world == 1) return imhd_create(Nx, Ny, Nz, device);
+    if (!nccl_unique_id) { set_error("imhd_create_slab: null NCCL unique id"); return nullptr; }
+    return wrap_engine(eng_create(Nx, Ny, Nz, world, 1, &rank, &device, nccl_unique_id), Nx, Ny, Nz, device);
+}
+
+extern "C" int imhd_ctx_num_slabs(imhd_ctx* c) { return !c ? 0 : (c->eng ? eng_nlocal(c->eng) : 1); }
+
+extern "C" int imhd_ctx_slab_extent(imhd_ctx* c, int q, int* k0, int* nzl, int* device) {
+    if (!c) { set_error("null context"); return IMHD_E_INVALID; }
+    if (c->eng) return eng_local_extent(c->eng, q, k0, nzl, device);
+    if (q != 0) { set_error("no such local slab %d", q); return IMHD_E_INVALID; }
+    if (k0) *k0 = 0;
+    if (nzl) *nzl = c->Nz;
+    if (device) *device = c->device;
+    return 0;
+}
+
+#define NOT_ON_SLABS(c, what)                                                                          \
+    do {                                                                                               \
+        if ((c) && (c)->eng) { set_error(what " is not available on a multi-slab context"); return IMHD_E_STATE; } \
+    } while (0)
+
 extern "C" void imhd_destroy(imhd_ctx* c) {
     if (!c) return;
+    if (c->eng) { eng_destroy(c->eng); delete c; return; }
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     cudaFree(c->buf[0]); cudaFree(c->buf[1]);
@@ -114,10 +167,7 @@ extern "C" void imhd_destroy(imhd_ctx* c) {
         c->cv->notify_all();
         c->writer->join();
         delete c->writer; delete c->jobs; delete c->mu; delete c->cv;
-        cudaFree(c->snap);
-        for (int s = 0; s < 2; ++s) { cudaFreeHost(c->pinned[s]); cudaEventDestroy(c->copy_done[s]); }
-        cudaEventDestroy(c->snap_done);
-        cudaStreamDestroy(c->copy_stream);
+        free_writer_buffers(c);
     }
     delete c;
 }
@@ -133,6 +183,11 @@ extern "C" int imhd_ctx_init_grids(imhd_ctx* c, float x_min, float x_max, float 
     CTX_CHECK(c);
     const float b[6] = {x_min, x_max, y_min, y_max, z_min, z_max};
     memcpy(c->bounds, b, sizeof(b));
+    if (c->eng) {
+        c->dx = (x_max - x_min) / (c->Nx - 1); c->dy = (y_max - y_min) / (c->Ny - 1); c->dz = (z_max - z_min) / (c->Nz - 1);
+        c->have_grids = true;
+        return eng_init_grids(c->eng, b);
+    }
     // fp32, as main.cu:98-100 / no_diffusion.cu:106-108
     c->dx = (x_max - x_min) / (c->Nx - 1);
     c->dy = (y_max - y_min) / (c->Ny - 1);
@@ -151,6 +206,7 @@ static int need_grids(imhd_ctx* c) {
 extern "C" int imhd_ctx_init_screwpinch_stride(imhd_ctx* c, float J0) {
     CTX_CHECK(c);
     if (int e = need_grids(c)) return e;
+    if (c->eng) return eng_init_ic(c->eng, 0, J0, 0.f);
     c->primed = false;
     return imhd_init_screwpinch_stride(c->buf[c->cur], J0, c->gx, c->gy, c->gz, c->Nx, c->Ny, c->Nz, c->stream);
 }
@@ -158,6 +214,7 @@ extern "C" int imhd_ctx_init_screwpinch_stride(imhd_ctx* c, float J0) {
 extern "C" int imhd_ctx_init_cubic_bennett_vortex_m0(imhd_ctx* c, float k, float A) {
     CTX_CHECK(c);
     if (int e = need_grids(c)) return e;
+    if (c->eng) return eng_init_ic(c->eng, 1, k, A);
     c->primed = false;
     return imhd_init_cubic_bennett_vortex_m0(c->buf[c->cur], k, A, c->gx, c->gy, c->gz, c->Nx, c->Ny, c->Nz, c->stream);
 }
@@ -172,6 +229,7 @@ struct IcEntry {
     const char* name;
     int nparams;
     int (*launch)(imhd_ctx*, const float*);
+    int ic;  // IC id of k_init_state (multi-slab contexts)
 };
 
 int ic_screwpinch(imhd_ctx* c, const float* p) {
@@ -193,11 +251,11 @@ int ic_zpinch(imhd_ctx* c, const float* p) {
 }
 
 const IcEntry kInitializers[] = {
-    {"screwpinch", 2, ic_screwpinch},                  // J0, r_max_coeff            configurers.hpp:21
-    {"screwpinch-stride", 1, ic_screwpinch_stride},    // J0                         :24
-    {"cubic-bennett-vortex", 0, ic_bennett},           //                            :27
-    {"cubic-bennett-vortex-m0", 2, ic_bennett_m0},     // k, A                       ext (no_diffusion.cu:168)
-    {"zpinch", 1, ic_zpinch},                          // r_max_coeff                ext (no_diffusion.cu:169)
+    {"screwpinch", 2, ic_screwpinch, 4},                  // J0, r_max_coeff            configurers.hpp:21
+    {"screwpinch-stride", 1, ic_screwpinch_stride, 0},    // J0                         :24
+    {"cubic-bennett-vortex", 0, ic_bennett, 2},           //                            :27
+    {"cubic-bennett-vortex-m0", 2, ic_bennett_m0, 1},     // k, A                       ext (no_diffusion.cu:168)
+    {"zpinch", 1, ic_zpinch, 3},                          // r_max_coeff                ext (no_diffusion.cu:169)
 };
 
 struct BundleEntry {
@@ -261,6 +319,7 @@ extern "C" int imhd_ctx_initialize(imhd_ctx* c, const char* sim_type, const floa
             set_error("imhd_ctx_initialize: \"%s\" takes %d parameter(s), got %d", e.name, e.nparams, nparams);
             return IMHD_E_INVALID;
         }
+        if (c->eng) return eng_init_ic(c->eng, e.ic, e.nparams > 0 ? params[0] : 0.f, e.nparams > 1 ? params[1] : 0.f);
         c->primed = false;
         return e.launch(c, params);
     }
@@ -293,6 +352,7 @@ extern "C" int imhd_registry_resolve_path(const char* corrector, const char* pre
 
 extern "C" int imhd_ctx_stability(imhd_ctx* c, float dt, imhd_stability* host_out) {
     CTX_CHECK(c);
+    if (c->eng) return eng_stability(c->eng, dt, host_out);
     imhd_slab s;
     memset(&s, 0, sizeof(s));
     s.Nx = c->Nx; s.Ny = c->Ny; s.Nz = c->Nz; s.k0 = 0; s.nzl = c->Nz; s.ghosts = 0;
@@ -303,6 +363,7 @@ extern "C" int imhd_ctx_stability(imhd_ctx* c, float dt, imhd_stability* host_ou
 extern "C" int imhd_ctx_set_state(imhd_ctx* c, const float* host_Q) {
     CTX_CHECK(c);
     if (!host_Q) { set_error("imhd_ctx_set_state: null host buffer"); return IMHD_E_INVALID; }
+    if (c->eng) return eng_set_state(c->eng, host_Q);
     c->primed = false;
     IMHD_CUDA(cudaMemcpyAsync(c->buf[c->cur], host_Q, 8 * c->cells * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     return 0;
@@ -311,12 +372,18 @@ extern "C" int imhd_ctx_set_state(imhd_ctx* c, const float* host_Q) {
 extern "C" int imhd_ctx_set_spacing(imhd_ctx* c, float dx, float dy, float dz) {
     CTX_CHECK(c);
     c->dx = dx; c->dy = dy; c->dz = dz;
+    if (c->eng) return eng_set_spacing(c->eng, dx, dy, dz);
     return 0;
 }
 
 extern "C" int imhd_ctx_prime(imhd_ctx* c, int path, float D, float dt) {
     CTX_CHECK(c);
     if (path != IMHD_PATH_A && path != IMHD_PATH_B) { set_error("imhd_ctx_prime: bad path %d", path); return IMHD_E_INVALID; }
+    if (c->eng) {
+        if (int e = eng_prime(c->eng, path, D, dt)) return e;
+        c->path = path; c->D = D; c->dt = dt; c->primed = true;
+        return 0;
+    }
     if (!(c->dx > 0.f) || !(c->dy > 0.f) || !(c->dz > 0.f)) {
         set_error("imhd_ctx_prime: grid spacing unset (call imhd_ctx_init_grids or imhd_ctx_set_spacing)");
         return IMHD_E_STATE;
@@ -343,6 +410,7 @@ extern "C" int imhd_ctx_prime(imhd_ctx* c, int path, float D, float dt) {
 
 extern "C" int imhd_ctx_step_granular(imhd_ctx* c, int nsteps) {
     CTX_CHECK(c);
+    NOT_ON_SLABS(c, "imhd_ctx_step_granular");
     if (!c->primed) { set_error("imhd_ctx_step_granular before imhd_ctx_prime"); return IMHD_E_STATE; }
     float* Q = c->buf[c->cur];
     float* Qi = c->buf[1 - c->cur];
@@ -358,6 +426,7 @@ extern "C" int imhd_ctx_step_granular(imhd_ctx* c, int nsteps) {
 
 extern "C" int imhd_ctx_step(imhd_ctx* c, int nsteps) {
     CTX_CHECK(c);
+    if (c->eng) return eng_step(c->eng, nsteps);
     if (!c->primed) { set_error("imhd_ctx_step before imhd_ctx_prime"); return IMHD_E_STATE; }
     imhd_slab s;
     s.Nx = c->Nx; s.Ny = c->Ny; s.Nz = c->Nz; s.k0 = 0; s.nzl = c->Nz; s.ghosts = 0;
@@ -382,6 +451,7 @@ extern "C" int imhd_ctx_step(imhd_ctx* c, int nsteps) {
 extern "C" int imhd_ctx_get_state(imhd_ctx* c, float* host_Q) {
     CTX_CHECK(c);
     if (!host_Q) { set_error("imhd_ctx_get_state: null host buffer"); return IMHD_E_INVALID; }
+    if (c->eng) return eng_get_state(c->eng, host_Q);
     IMHD_CUDA(cudaMemcpyAsync(host_Q, c->buf[c->cur], 8 * c->cells * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     IMHD_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
@@ -389,6 +459,7 @@ extern "C" int imhd_ctx_get_state(imhd_ctx* c, float* host_Q) {
 
 extern "C" int imhd_ctx_get_grids(imhd_ctx* c, float* x, float* y, float* z) {
     CTX_CHECK(c);
+    NOT_ON_SLABS(c, "imhd_ctx_get_grids");
     if (int e = need_grids(c)) return e;
     IMHD_CUDA(cudaMemcpyAsync(x, c->gx, sizeof(float) * c->Nx, cudaMemcpyDeviceToHost, c->stream));
     IMHD_CUDA(cudaMemcpyAsync(y, c->gy, sizeof(float) * c->Ny, cudaMemcpyDeviceToHost, c->stream));
@@ -397,11 +468,25 @@ extern "C" int imhd_ctx_get_grids(imhd_ctx* c, float* x, float* y, float* z) {
     return 0;
 }
 
-extern "C" float* imhd_ctx_device_state(imhd_ctx* c) { return c ? c->buf[c->cur] : nullptr; }
-extern "C" void* imhd_ctx_stream(imhd_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" float* imhd_ctx_device_state(imhd_ctx* c) { return !c ? nullptr : (c->eng ? eng_device_state(c->eng, 0) : c->buf[c->cur]); }
+extern "C" void* imhd_ctx_stream(imhd_ctx* c) { return !c ? nullptr : (c->eng ? eng_stream(c->eng, 0) : (void*)c->stream); }
+
+// slab-local state transfer of a multi-slab context: the owned planes (8, nzl, Nx, Ny) of local slab q, host memory.
+// After imhd_ctx_set_state_local on every slab (of every process) the next imhd_ctx_prime refreshes the ghost planes.
+extern "C" int imhd_ctx_set_state_local(imhd_ctx* c, int q, const float* host_slab) {
+    CTX_CHECK(c);
+    if (!c->eng) return q == 0 ? imhd_ctx_set_state(c, host_slab) : IMHD_E_INVALID;
+    return eng_set_state_local(c->eng, q, host_slab);
+}
+extern "C" int imhd_ctx_get_state_local(imhd_ctx* c, int q, float* host_slab) {
+    CTX_CHECK(c);
+    if (!c->eng) return q == 0 ? imhd_ctx_get_state(c, host_slab) : IMHD_E_INVALID;
+    return eng_get_state_local(c->eng, q, host_slab);
+}
 
 extern "C" int imhd_ctx_synchronize(imhd_ctx* c) {
     CTX_CHECK(c);
+    if (c->eng) return eng_synchronize(c->eng);
     IMHD_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -435,23 +520,45 @@ static void writer_main(imhd_ctx* c) {
         const int rc = imhd_h5_write_fluidvars(job.path.c_str(), c->pinned[job.slot], c->Nx, c->Ny, c->Nz, job.attrs);
         {
             std::lock_guard<std::mutex> g(*c->mu);
-            if (rc) ++c->write_errors;
+            if (rc) {
+                ++c->write_errors;
+                snprintf(c->write_error_text, sizeof(c->write_error_text), "%s", imhd_last_error());
+            }
             c->slot_busy[job.slot] = false;
         }
         c->cv->notify_all();
     }
 }
 
+static void free_writer_buffers(imhd_ctx* c) {
+    cudaFree(c->snap); c->snap = nullptr;
+    for (int s = 0; s < 2; ++s) {
+        if (c->pinned[s]) cudaFreeHost(c->pinned[s]);
+        if (c->copy_done[s]) cudaEventDestroy(c->copy_done[s]);
+        c->pinned[s] = nullptr; c->copy_done[s] = nullptr;
+    }
+    if (c->snap_done) cudaEventDestroy(c->snap_done);
+    if (c->snap_free) cudaEventDestroy(c->snap_free);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    c->snap_done = c->snap_free = nullptr; c->copy_stream = nullptr;
+}
+
 static int start_writer(imhd_ctx* c) {
     if (c->writer) return 0;
     const size_t bytes = 8 * c->cells * sizeof(float);
-    IMHD_CUDA(cudaMalloc(&c->snap, bytes));
-    for (int s = 0; s < 2; ++s) {
-        IMHD_CUDA(cudaMallocHost(&c->pinned[s], bytes));
-        IMHD_CUDA(cudaEventCreateWithFlags(&c->copy_done[s], cudaEventDisableTiming));
+    bool ok = cudaMalloc(&c->snap, bytes) == cudaSuccess;
+    for (int s = 0; s < 2 && ok; ++s)
+        ok = cudaMallocHost(&c->pinned[s], bytes) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->copy_done[s], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->snap_done, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->snap_free, cudaEventDisableTiming) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) {  // roll back: nothing half-allocated survives, the next call starts from scratch
+        const int e = cuda_fail(cudaGetLastError(), "output staging allocation", __FILE__, __LINE__);
+        free_writer_buffers(c);
+        return e ? e : IMHD_E_STATE;
     }
-    IMHD_CUDA(cudaEventCreateWithFlags(&c->snap_done, cudaEventDisableTiming));
-    IMHD_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    c->snap_used = false;
     c->jobs = new std::deque<imhd_ctx::Job>();
     c->mu = new std::mutex();
     c->cv = new std::condition_variable();
@@ -461,9 +568,11 @@ static int start_writer(imhd_ctx* c) {
 
 // Queue frame `frame` of the current state for output as <dir>fluidvars_<frame>.h5 (attributes on frame 0 only, as
 // main.cu:141-145).  Returns at once: a device-side snapshot (1 copy at HBM speed) decouples the time loop from the
-// D2H copy and the file write, which run on a copy stream and a writer thread.
+// D2H copy and the file write, which run on a copy stream and a writer thread.  The compute stream only ever waits
+// for the PREVIOUS frame's D2H copy (before it overwrites the snapshot buffer), never for this frame's.
 extern "C" int imhd_ctx_write_frame(imhd_ctx* c, const char* dir, int frame) {
     CTX_CHECK(c);
+    NOT_ON_SLABS(c, "imhd_ctx_write_frame (gather with imhd_ctx_get_state and use imhd_h5_write_fluidvars)");
     if (!dir) { set_error("imhd_ctx_write_frame: null directory"); return IMHD_E_INVALID; }
     if (int e = start_writer(c)) return e;
     const int slot = c->next_slot;
@@ -473,14 +582,20 @@ extern "C" int imhd_ctx_write_frame(imhd_ctx* c, const char* dir, int frame) {
         c->slot_busy[slot] = true;
     }
     const size_t bytes = 8 * c->cells * sizeof(float);
-    IMHD_CUDA(cudaStreamWaitEvent(c->stream, c->copy_done[slot], 0));  // snapshot buffer free again?
-    IMHD_CUDA(cudaMemcpyAsync(c->snap, c->buf[c->cur], bytes, cudaMemcpyDeviceToDevice, c->stream));
-    IMHD_CUDA(cudaEventRecord(c->snap_done, c->stream));
-    IMHD_CUDA(cudaStreamWaitEvent(c->copy_stream, c->snap_done, 0));
-    IMHD_CUDA(cudaMemcpyAsync(c->pinned[slot], c->snap, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
-    IMHD_CUDA(cudaEventRecord(c->copy_done[slot], c->copy_stream));
-    // the NEXT snapshot must not overwrite `snap` before this D2H has drained it
-    IMHD_CUDA(cudaStreamWaitEvent(c->stream, c->copy_done[slot], 0));
+    cudaError_t e = cudaSuccess;
+    if (c->snap_used) e = cudaStreamWaitEvent(c->stream, c->snap_free, 0);  // previous frame drained out of `snap`?
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->snap, c->buf[c->cur], bytes, cudaMemcpyDeviceToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(c->snap_done, c->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->snap_done, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->pinned[slot], c->snap, bytes, cudaMemcpyDeviceToHost, c->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(c->copy_done[slot], c->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(c->snap_free, c->copy_stream);
+    if (e != cudaSuccess) {  // give the slot back, or the next frame on it (and flush) would wait for ever
+        { std::lock_guard<std::mutex> g(*c->mu); c->slot_busy[slot] = false; }
+        c->cv->notify_all();
+        return cuda_fail(e, "imhd_ctx_write_frame", __FILE__, __LINE__);
+    }
+    c->snap_used = true;
     {
         std::lock_guard<std::mutex> g(*c->mu);
         c->jobs->push_back({slot, frame, frame == 0 ? 1 : 0, std::string(dir) + "fluidvars_" + std::to_string(frame) + ".h5"});
@@ -496,12 +611,17 @@ extern "C" int imhd_ctx_flush_output(imhd_ctx* c) {
     if (!c->writer) return 0;
     std::unique_lock<std::mutex> lk(*c->mu);
     c->cv->wait(lk, [&] { return c->jobs->empty() && !c->slot_busy[0] && !c->slot_busy[1]; });
-    if (c->write_errors) { set_error("%d frame(s) could not be written", c->write_errors); return IMHD_E_IO; }
+    if (c->write_errors) {
+        set_error("%d frame(s) could not be written; last error: %s", c->write_errors, c->write_error_text);
+        return IMHD_E_IO;
+    }
     return 0;
 }
 
 extern "C" int imhd_ctx_write_grid(imhd_ctx* c, const char* dir) {
     CTX_CHECK(c);
+    if (!dir) { set_error("imhd_ctx_write_grid: null directory"); return IMHD_E_INVALID; }
+    NOT_ON_SLABS(c, "imhd_ctx_write_grid");
     if (int e = need_grids(c)) return e;
     std::vector<float> x(c->Nx), y(c->Ny), z(c->Nz);
     if (int e = imhd_ctx_get_grids(c, x.data(), y.data(), z.data())) return e;

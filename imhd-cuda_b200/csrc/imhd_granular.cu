@@ -254,7 +254,9 @@ __device__ __forceinline__ float total_energy(const float U[8], float p) {  // :
 //     4 ScrewPinch(a=J0,b=r_max_coeff)   (initialize_od.cu:269, 132, 59, 347, 207)
 template <int IC>
 __global__ void __launch_bounds__(256) k_init_state(float* __restrict__ Q, float a, float b, const float* __restrict__ gx,
-                                                    const float* __restrict__ gy, const float* __restrict__ gz, Params P) {
+                                                    const float* __restrict__ gy, const float* __restrict__ gz, Params P,
+                                                    int kofs = 0) {
+    // kofs: global index of array plane 0 (z-slab arrays of the multi-GPU engine); gz is the array's own z grid
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y * blockDim.y + threadIdx.y;
     const int k = blockIdx.z;
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(256) k_init_state(float* __restrict__ Q, float
             if (IC == 1) {
                 const float z = gz[k];
                 const float p = (float)(1 - phi3 / sqd(phi + 1) * (phi - 10));      // :180
-                U[RHO] = (float)(1.0 + b * cosf(k * z));  // the z loop index shadows the wavenumber (:158,183)
+                U[RHO] = (float)(1.0 + b * cosf((k + kofs) * z));  // the z loop index shadows the wavenumber (:158,183)
                 U[MZ] = (float)((1) * r2 / sqd(phi + 1));
                 U[BX] = Br * x - Btheta * y / phi;
                 U[BY] = Br * y + Btheta * x / phi;
@@ -434,6 +436,62 @@ extern "C" int imhd_init_screwpinch(float* Q, float J0, float r_max_coeff, const
     if (int e = bad_dims(Nx, Ny, Nz)) return e;
     const Params P = make_params(0, 0.f, 1.f, 1.f, 1.f, 1.f, Nx, Ny, Nz);
     k_init_state<4><<<cell_grid(P, Nz), kCellBlock, 0, (cudaStream_t)stream>>>(Q, J0, r_max_coeff, x, y, z, P);
+    IMHD_LAUNCH_CHECK(1);
+    return 0;
+}
+
+// Internal (multi-GPU engine): initial condition `ic` (the IC ids of k_init_state) on a z-slab array of nz_array planes
+// whose plane 0 is global plane kofs; z = the array's own grid.  Same kernel, same bits as the full-domain call.
+int imhd_init_ic_slab(int ic, float* Q, float a, float b, const float* x, const float* y, const float* z, int Nx, int Ny,
+                      int nz_array, int kofs, void* stream) {
+    const Params P = make_params(0, 0.f, 1.f, 1.f, 1.f, 1.f, Nx, Ny, nz_array);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ic) {
+        case 0: k_init_state<0><<<cell_grid(P, nz_array), kCellBlock, 0, st>>>(Q, a, b, x, y, z, P, kofs); break;
+        case 1: k_init_state<1><<<cell_grid(P, nz_array), kCellBlock, 0, st>>>(Q, a, b, x, y, z, P, kofs); break;
+        case 2: k_init_state<2><<<cell_grid(P, nz_array), kCellBlock, 0, st>>>(Q, a, b, x, y, z, P, kofs); break;
+        case 3: k_init_state<3><<<cell_grid(P, nz_array), kCellBlock, 0, st>>>(Q, a, b, x, y, z, P, kofs); break;
+        case 4: k_init_state<4><<<cell_grid(P, nz_array), kCellBlock, 0, st>>>(Q, a, b, x, y, z, P, kofs); break;
+        default: set_error("unknown initial-condition id %d", ic); return IMHD_E_INVALID;
+    }
+    IMHD_LAUNCH_CHECK(1);
+    return 0;
+}
+
+// rigidConductingWallBCsLeftRight (kernels_fluidbcs.cu:436-465) on array planes [ka, kb) of a slab array
+namespace imhd {
+__global__ void k_wall_leftright_planes(float* __restrict__ Q, Params P, int ka, int kb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = ka + blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= P.Nx || k >= kb) return;
+    const long long vs = P.cube;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const long long l = (long long)k * P.plane + (long long)i * P.Ny + (side ? P.Ny - 1 : 0);
+        Q[l] = 1.0f;
+#pragma unroll
+        for (int v = 1; v < 7; ++v) Q[l + v * vs] = 0.0f;
+        Q[l + EN * vs] = wall_e(Q[l + EN * vs]);
+    }
+}
+}  // namespace imhd
+int imhd_wall_leftright_planes(float* Q, int Nx, int Ny, int nz_array, int ka, int kb, void* stream) {
+    if (kb <= ka) return 0;
+    const Params P = make_params(0, 0.f, 1.f, 1.f, 1.f, 1.f, Nx, Ny, nz_array);
+    imhd::k_wall_leftright_planes<<<dim3((Nx + 15) / 16, (kb - ka + 15) / 16), dim3(16, 16), 0, (cudaStream_t)stream>>>(Q, P, ka, kb);
+    IMHD_LAUNCH_CHECK(1);
+    return 0;
+}
+
+// z grid of a slab array: plane kk holds z_min + (kofs + kk) * dz evaluated exactly like the full grid (k_init_axis)
+namespace imhd {
+__global__ void k_init_axis_ofs(float* __restrict__ g, float lo, float d, int n, int ofs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) g[i] = lo + (unsigned)max(i + ofs, 0) * d;
+}
+}  // namespace imhd
+int imhd_init_axis_slab(float* g, float lo, float d, int n, int ofs, void* stream) {
+    imhd::k_init_axis_ofs<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, lo, d, n, ofs);
     IMHD_LAUNCH_CHECK(1);
     return 0;
 }

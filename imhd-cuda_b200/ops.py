@@ -201,6 +201,13 @@ def step_full_domain(Qin, Qout, path, D, dt, dx, dy, dz, corner_e=0.0):
     step_fused(Qin, Qout, q0, q0, wrap, s)
 
 
+def nccl_unique_id() -> bytes:
+    """128 bytes identifying one NCCL clique: made by ONE process, handed to every process of Context.slab."""
+    buf = C.create_string_buffer(128)
+    check(_lib.load().imhd_nccl_unique_id(buf, 128))
+    return buf.raw
+
+
 def launch_count() -> int:
     return int(_lib.load().imhd_launch_count())
 
@@ -209,12 +216,49 @@ def launch_count() -> int:
 class Context:
     """``imhd_ctx``: what src/on-device/main.cu / no_diffusion.cu own between their IC and their time loop."""
 
-    def __init__(self, Nx: int, Ny: int, Nz: int, device: int = 0):
+    def __init__(self, Nx: int, Ny: int, Nz: int, device: int = 0, _handle=None):
         self.L = _lib.load()
         self.Nx, self.Ny, self.Nz = Nx, Ny, Nz
-        self.h = self.L.imhd_create(Nx, Ny, Nz, device)
+        self.h = _handle if _handle is not None else self.L.imhd_create(Nx, Ny, Nz, device)
         if not self.h:
             raise _lib.ImhdError(-1, self.L.imhd_last_error().decode())
+
+    # ---- multi-GPU contexts: the z-slab time loop in C++ behind the same calls (imhd_create_multi / imhd_create_slab) ----
+    @classmethod
+    def multi(cls, Nx: int, Ny: int, Nz: int, n_gpus: int, devices=None):
+        """The whole domain as n_gpus z-slabs driven from this process (one slab per device)."""
+        L = _lib.load()
+        arr = (C.c_int * n_gpus)(*(devices if devices is not None else range(n_gpus)))
+        return cls(Nx, Ny, Nz, _handle=L.imhd_create_multi(Nx, Ny, Nz, n_gpus, arr) or 0)
+
+    @classmethod
+    def slab(cls, Nx: int, Ny: int, Nz: int, rank: int, world: int, device: int, unique_id: bytes):
+        """Slab `rank` of `world` in this process (one process per GPU); unique_id from nccl_unique_id() of one process."""
+        L = _lib.load()
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        return cls(Nx, Ny, Nz, _handle=L.imhd_create_slab(Nx, Ny, Nz, rank, world, device, buf) or 0)
+
+    @property
+    def num_slabs(self) -> int:
+        return int(self.L.imhd_ctx_num_slabs(self.h))
+
+    def slab_extent(self, q: int = 0):
+        """(k0, nzl, device) of local slab q."""
+        k0, nzl, dev = C.c_int(), C.c_int(), C.c_int()
+        check(self.L.imhd_ctx_slab_extent(self.h, q, C.byref(k0), C.byref(nzl), C.byref(dev)))
+        return k0.value, nzl.value, dev.value
+
+    def set_state_local(self, Q: np.ndarray, q: int = 0):
+        Q = np.ascontiguousarray(Q, dtype=np.float32)
+        assert Q.shape == (8, self.slab_extent(q)[1], self.Nx, self.Ny)
+        check(self.L.imhd_ctx_set_state_local(self.h, q, Q.ctypes.data_as(C.c_void_p)))
+        check(self.L.imhd_ctx_synchronize(self.h))
+
+    def get_state_local(self, q: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((8, self.slab_extent(q)[1], self.Nx, self.Ny), np.float32)
+        check(self.L.imhd_ctx_get_state_local(self.h, q, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def close(self):
         if getattr(self, "h", None):

@@ -233,6 +233,32 @@ int imhd_ctx_write_frame(imhd_ctx* ctx, const char* dir, int frame);
 int imhd_ctx_flush_output(imhd_ctx* ctx);
 int imhd_ctx_write_grid(imhd_ctx* ctx, const char* dir);
 
+/* ---- multi-GPU: the z-slab time loop behind the same context functions -----------------------------
+ * The reference is single-GPU (its host loop: src/on-device/main.cu:196-238 / no_diffusion.cu:284-337); these two
+ * constructors give that loop a domain cut into z-slabs, one per GPU, ghost planes and predictor planes exchanged
+ * between ring neighbours over NVLink (ncclSend/ncclRecv on a side stream, under the interior launch).  Every
+ * imhd_ctx_* function above works on such a context and means the WHOLE domain (init_grids, the initial conditions,
+ * set_state / get_state with full (8,Nz,Nx,Ny) host arrays, prime, step, stability, synchronize, imhd_run_host);
+ * results are bit-identical to the single-GPU context.  Not available on it: imhd_ctx_step_granular,
+ * imhd_ctx_get_grids, imhd_ctx_write_frame / write_grid (gather with imhd_ctx_get_state and call
+ * imhd_h5_write_fluidvars).  NCCL is bound at run time (dlopen libnccl.so.2); single-GPU use does not need it.
+ *   imhd_create_multi : all n_gpus slabs in THIS process, slab q on devices[q] (NULL = devices 0..n_gpus-1)
+ *   imhd_create_slab  : slab `rank` of `world` in this process (one process per GPU, e.g. under torchrun);
+ *                       nccl_unique_id = the 128 bytes one process obtained from imhd_nccl_unique_id. */
+imhd_ctx* imhd_create_multi(int Nx, int Ny, int Nz, int n_gpus, const int* devices);
+imhd_ctx* imhd_create_slab(int Nx, int Ny, int Nz, int rank, int world, int device, const void* nccl_unique_id);
+int imhd_nccl_unique_id(void* id_out, int bytes); /* bytes >= 128 */
+/* Slabs held by this context (1 for a single-GPU or imhd_create_slab context) and their owned global planes
+ * [k0, k0+nzl) / device. */
+int imhd_ctx_num_slabs(imhd_ctx* ctx);
+int imhd_ctx_slab_extent(imhd_ctx* ctx, int q, int* k0, int* nzl, int* device);
+/* Slab-local transfers: the owned planes (8, nzl, Nx, Ny) of local slab q from / to host memory (a process that holds
+ * one slab never needs the full array).  Ghost planes are refreshed by the next imhd_ctx_prime. */
+int imhd_ctx_set_state_local(imhd_ctx* ctx, int q, const float* host_slab);
+int imhd_ctx_get_state_local(imhd_ctx* ctx, int q, float* host_slab);
+/* Tuning hook: planes next to each slab end that are launched ahead of the interior (>= 3; default 4). */
+void imhd_set_edge_planes(int planes);
+
 /* Whole job through HOST buffers (the e2e path bench.py times): upload host_Q_in, prime,
  * run nsteps fused steps, download into host_Q_out.  Both buffers 8*Nx*Ny*Nz floats. */
 int imhd_run_host(imhd_ctx* ctx, const float* host_Q_in, float* host_Q_out, int path, float D,

@@ -364,6 +364,7 @@ class ThreadRing:
 
         def ring_exchange(send_up, send_down, recv_from_down, recv_from_up, up, down):
             ring.box[(rank, "up")], ring.box[(rank, "down")] = send_up, send_down
+            torch_sync()   # the sender's kernels (its own, possibly non-blocking, stream) finish before a peer copies
             ring.bar.wait()
             recv_from_down.copy_(ring.box[(down, "up")])
             recv_from_up.copy_(ring.box[(up, "down")])

@@ -68,7 +68,7 @@ def test_reference_on_gpu_agrees_with_its_host_build_and_with_granular(imhd, tor
     eq = np.isclose(Qg, Qh, rtol=0, atol=0, equal_nan=True)
     err = oracle_mod.normalised_linf(np.nan_to_num(Qg), np.nan_to_num(Qh)).max()
     print(f"\nreference sm_100 (-fmad=false) vs reference host, path {tag} {ic}: bit-equal cells {eq.mean():.6f}, nLinf {err:.2e}")
-    assert err <= 1e-6
+    assert eq.all()   # exact, NaN == NaN (the random state drives a few cells non-finite in both builds alike)
 
     # our parity-granular operators through the C ABI
     with imhd.ops.Context(*dims) as ctx:
@@ -78,8 +78,9 @@ def test_reference_on_gpu_agrees_with_its_host_build_and_with_granular(imhd, tor
         ctx.step_granular(nsteps)
         Qo = ctx.get_state()
     err2 = oracle_mod.normalised_linf(np.nan_to_num(Qo), np.nan_to_num(Qg)).max()
-    print(f"granular (C ABI) vs reference sm_100 (-fmad=false): bit-equal {bits_equal(Qo, Qg)}, nLinf {err2:.2e}")
-    assert err2 <= 1e-6
+    eq2 = np.isclose(Qo, Qg, rtol=0, atol=0, equal_nan=True)
+    print(f"granular (C ABI) vs reference sm_100 (-fmad=false): bit-equal {bits_equal(Qo, Qg)}, equal cells {eq2.mean():.6f}, nLinf {err2:.2e}")
+    assert eq2.all()
 
 
 @pytest.mark.parametrize("tag", ["A", "B"])
@@ -100,6 +101,43 @@ def test_fused_c1_100_steps_vs_reference_kernels_on_the_same_gpu(imhd, torch, O,
     err = oracle_mod.normalised_linf(Qf, Qr)
     print(f"\nfused vs reference kernels on sm_100 (stock flags), C1 path {tag}, 100 steps: nLinf per variable {err}")
     assert err.max() <= TOL
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_production_grid_100_steps_vs_reference_kernels_on_the_same_gpu(imhd, torch, oracle_mod, tag):
+    """north_star bar at the production size: 304x304x592 (BASELINE configs[1]), 100 steps, per-variable normalised
+    L-inf <= 1e-5 against the reference's unmodified kernels (stock flags) run on the same B200 in the launch order of
+    src/on-device/main.cu:196-213 (path B, D = 0.01) / no_diffusion.cu:284-312 (path A).  ~1 min: the reference needs
+    ~0.5 s per step with diffusion at this size."""
+    from conftest import BOUNDS
+
+    G = refgpu(oracle_mod, nofma=False)
+    path, D = (oracle_mod.PATH_A, 0.0) if tag == "A" else (oracle_mod.PATH_B, D_B)
+    Nx, Ny, Nz = 304, 304, 592
+    geom = G.COVER_A if tag == "A" else G.COVER_B
+    assert G.covers(geom, Nx, Ny, Nz)
+    free_b, _ = torch.cuda.mem_get_info()
+    if free_b < 12 * (1 << 30):
+        pytest.skip("needs ~9 GB of device memory")
+    with imhd.ops.Context(Nx, Ny, Nz) as ctx:
+        ctx.init_grids(*BOUNDS)
+        ctx.init_screwpinch_stride(1.0)
+        Q0 = ctx.get_state()
+        d = tuple(float(oracle_mod.grid_spacing(BOUNDS[2 * a], BOUNDS[2 * a + 1], n)) for a, n in enumerate((Nx, Ny, Nz)))
+        Q = torch.from_numpy(Q0).cuda()
+        Qint = torch.zeros_like(Q)
+        G.prime(Q.data_ptr(), Qint.data_ptr(), (Nx, Ny, Nz), path, D, DT, *d, geom)
+        G.steps(Q.data_ptr(), Qint.data_ptr(), (Nx, Ny, Nz), path, 100, D, DT, *d, geom)
+        torch.cuda.synchronize()
+        del Qint
+        ctx.prime(path, D, DT)
+        ctx.step(100)
+        Qf = torch.from_numpy(ctx.get_state()).cuda()
+    assert bool(torch.isfinite(Q).all()) and bool(torch.isfinite(Qf).all())
+    err = [float((Qf[v] - Q[v]).abs().max() / Q[v].abs().max()) for v in range(8)]
+    print(f"\nfused vs reference kernels on sm_100 (stock flags), 304x304x592 path {tag}, 100 steps: nLinf per variable "
+          + " ".join(f"{e:.2e}" for e in err))
+    assert max(err) <= TOL
 
 
 def test_initial_condition_kernels_vs_reference_kernels_on_the_gpu(imhd, torch, O, oracle_mod):
@@ -123,6 +161,4 @@ def test_initial_condition_kernels_vs_reference_kernels_on_the_gpu(imhd, torch, 
         eq = bits_equal(Q.cpu().numpy(), Qr.cpu().numpy())
         err = np.abs(Q.cpu().numpy().astype(np.float64) - Qr.cpu().numpy()).max()
         print(f"\n{key}: bit-identical to the reference kernel on sm_100 = {eq} (max abs diff {err:.2e})")
-        assert err <= 5e-7, key
-        if key in ("screwpinch-stride", "zpinch", "screwpinch"):
-            assert eq, key
+        assert eq, key
