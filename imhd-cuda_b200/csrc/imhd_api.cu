@@ -572,7 +572,13 @@ static int start_writer(imhd_ctx* c) {
 // for the PREVIOUS frame's D2H copy (before it overwrites the snapshot buffer), never for this frame's.
 extern "C" int imhd_ctx_write_frame(imhd_ctx* c, const char* dir, int frame) {
     CTX_CHECK(c);
-    NOT_ON_SLABS(c, "imhd_ctx_write_frame (gather with imhd_ctx_get_state and use imhd_h5_write_fluidvars)");
+    if (c->eng) {  // multi-slab context: gather the slabs into one host array and write it (synchronous)
+        if (!dir) { set_error("imhd_ctx_write_frame: null directory"); return IMHD_E_INVALID; }
+        std::vector<float> host(8 * c->cells);
+        if (int e = eng_get_state(c->eng, host.data())) return e;
+        return imhd_h5_write_fluidvars((std::string(dir) + "fluidvars_" + std::to_string(frame) + ".h5").c_str(), host.data(), c->Nx,
+                                       c->Ny, c->Nz, frame == 0 ? 1 : 0);
+    }
     if (!dir) { set_error("imhd_ctx_write_frame: null directory"); return IMHD_E_INVALID; }
     if (int e = start_writer(c)) return e;
     const int slot = c->next_slot;
@@ -621,8 +627,14 @@ extern "C" int imhd_ctx_flush_output(imhd_ctx* c) {
 extern "C" int imhd_ctx_write_grid(imhd_ctx* c, const char* dir) {
     CTX_CHECK(c);
     if (!dir) { set_error("imhd_ctx_write_grid: null directory"); return IMHD_E_INVALID; }
-    NOT_ON_SLABS(c, "imhd_ctx_write_grid");
     if (int e = need_grids(c)) return e;
+    if (c->eng) {  // the same fp32 expression as the device kernel (x[i] = x_min + i * dx, initialize_od.cu:26-57)
+        std::vector<float> x(c->Nx), y(c->Ny), z(c->Nz);
+        for (int i = 0; i < c->Nx; ++i) { volatile float t = (float)(unsigned)i * c->dx; x[i] = c->bounds[0] + t; }
+        for (int i = 0; i < c->Ny; ++i) { volatile float t = (float)(unsigned)i * c->dy; y[i] = c->bounds[2] + t; }
+        for (int i = 0; i < c->Nz; ++i) { volatile float t = (float)(unsigned)i * c->dz; z[i] = c->bounds[4] + t; }
+        return imhd_h5_write_grid((std::string(dir) + "grid.h5").c_str(), x.data(), y.data(), z.data(), c->Nx, c->Ny, c->Nz);
+    }
     std::vector<float> x(c->Nx), y(c->Ny), z(c->Nz);
     if (int e = imhd_ctx_get_grids(c, x.data(), y.data(), z.data())) return e;
     return imhd_h5_write_grid((std::string(dir) + "grid.h5").c_str(), x.data(), y.data(), z.data(), c->Nx, c->Ny, c->Nz);

@@ -7,7 +7,9 @@
 // The execution-configuration arguments (block dims, SM multipliers) are accepted and ignored: the library picks its
 // own tiling.  The writer/attribute/grid binary names and num_proc are accepted and unused (output is in-process);
 // eigen_bin_name other than "none" runs the CFL scan on the device (imhd_ctx_stability) and prints the scanner's report.
-// Optional environment: IMHD_OUTPUT_EVERY=n (default 1 = the reference's behaviour), IMHD_DEVICE=d,
+// Optional environment: IMHD_OUTPUT_EVERY=n (default 1 = the reference's behaviour), IMHD_DEVICE=d, IMHD_GPUS=N (the
+// domain as N z-slabs on devices 0..N-1 of this box, exchanged over NVLink: imhd_create_multi; output is then gathered
+// and written synchronously),
 // IMHD_IC=<registry key>[:p0[,p1]] selects the initial condition by the reference's registry key
 // (include/on-device/utils/configurers.hpp:21-29) instead of the one each shipped driver hard-codes; parameters left
 // out come from argv (J0, r_max_coeff, A, k_harmonic) where the argv list has them.
@@ -59,7 +61,9 @@ int main(int argc, char* argv[]) {
     env = getenv("IMHD_DEVICE");
     const int device = env ? atoi(env) : 0;
 
-    imhd_ctx* ctx = imhd_create(Nx, Ny, Nz, device);
+    env = getenv("IMHD_GPUS");
+    const int n_gpus = env && atoi(env) > 1 ? atoi(env) : 1;
+    imhd_ctx* ctx = n_gpus > 1 ? imhd_create_multi(Nx, Ny, Nz, n_gpus, nullptr) : imhd_create(Nx, Ny, Nz, device);
     if (!ctx) { fprintf(stderr, "%s\n", imhd_last_error()); return EXIT_FAILURE; }
     CHECK(imhd_ctx_init_grids(ctx, x_min, x_max, y_min, y_max, z_min, z_max));
 #ifdef IMHD_NODIFF

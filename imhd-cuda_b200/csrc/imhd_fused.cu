@@ -31,6 +31,9 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <mutex>
+#include <vector>
+
 #include "imhd_common.cuh"
 
 namespace imhd {
@@ -1226,6 +1229,59 @@ struct PairLaunch {
     static auto kernel() { return k_fused_pair<PATH, TI>; }
 };
 
+// ---- optional per-launch timing of the hot kernel (bench.py's roofline leg) ---------------------------------------------
+// When enabled, every launch of the marching kernel that covers >= 64 planes (+ its remainder strip) is bracketed by
+// a CUDA event pair on the launching stream; imhd_fused_timing_read sums them after the caller has synchronised.
+namespace {
+struct TimedLaunch { cudaEvent_t a, b; int dev; long long cells; };
+std::vector<TimedLaunch>* g_timed = nullptr;
+std::mutex g_timed_mu;
+bool g_timing = false;
+}  // namespace
+
+extern "C" void imhd_fused_timing(int enable) {
+    std::lock_guard<std::mutex> g(g_timed_mu);
+    if (!g_timed) { g_timed = new std::vector<TimedLaunch>(); g_timed->reserve(100000); }  // pointers into it stay valid
+    for (TimedLaunch& t : *g_timed) { cudaSetDevice(t.dev); cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    g_timed->clear();
+    g_timing = enable != 0;
+}
+
+// total_ms / launches / cell_updates of the bracketed launches since imhd_fused_timing(1); synchronise the streams first
+extern "C" int imhd_fused_timing_read(double* total_ms, int* launches, long long* cell_updates) {
+    std::lock_guard<std::mutex> g(g_timed_mu);
+    double ms = 0.0;
+    long long cells = 0;
+    int n = 0;
+    if (g_timed)
+        for (TimedLaunch& t : *g_timed) {
+            float x = 0.f;
+            cudaSetDevice(t.dev);
+            if (cudaEventElapsedTime(&x, t.a, t.b) != cudaSuccess) { cudaGetLastError(); continue; }
+            ms += x; cells += t.cells; ++n;
+        }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = n;
+    if (cell_updates) *cell_updates = cells;
+    return 0;
+}
+
+static TimedLaunch* timing_begin(const FusedArgs& A, int nz, cudaStream_t st) {
+    if (!g_timing || nz < 64) return nullptr;
+    std::lock_guard<std::mutex> g(g_timed_mu);
+    if (!g_timed || g_timed->size() >= 100000) return nullptr;
+    TimedLaunch t;
+    cudaGetDevice(&t.dev);
+    t.cells = (long long)A.P.Nx * A.P.Ny * nz;
+    if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return nullptr;
+    cudaEventRecord(t.a, st);
+    g_timed->push_back(t);
+    return &g_timed->back();
+}
+static void timing_end(TimedLaunch* t, cudaStream_t st) {
+    if (t) cudaEventRecord(t->b, st);
+}
+
 template <int PATH, class L>
 static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, cudaStream_t st) {
     using G = typename L::G;
@@ -1249,6 +1305,7 @@ static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, cudaStream_t st) {
     const int nchunk = pick_chunk(A, nz, (long long)A.ntile_i * grid_j);
     static unsigned long long done = 0;
     if (int e = ensure_smem(L::kernel(), G::SMEM, done)) return e;
+    TimedLaunch* timed = timing_begin(A, nz, st);
     L::kernel()<<<dim3(grid_j, A.ntile_i, nchunk), dim3(32, L::THREAD_ROWS), G::SMEM, st>>>(A, tmap);
     IMHD_LAUNCH_CHECK(1);
     if (strip) {
@@ -1271,6 +1328,7 @@ static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, cudaStream_t st) {
         k_fused_strip<PATH><<<dim3(S.ntile_i, 1, (nz + S.chunk - 1) / S.chunk), dim3(32, strip_rows), strip_smem, st>>>(S);
         IMHD_LAUNCH_CHECK(1);
     }
+    timing_end(timed, st);
     return 0;
 }
 

@@ -162,6 +162,12 @@ float imhd_wall_energy_fixed_point(float e, int max_iter);
 void imhd_set_chunk(int planes);
 void imhd_set_kernel_variant(int flags);
 
+/* Measurement hook (bench.py's roofline leg): while enabled, every launch of the marching kernel over >= 64 planes
+ * (with its remainder strip) is bracketed by a CUDA event pair on the launching stream; after synchronising, read the
+ * summed duration, the number of launches and the cell-updates they covered.  imhd_fused_timing(0|1) also resets. */
+void imhd_fused_timing(int enable);
+int imhd_fused_timing_read(double* total_ms, int* launches, long long* cell_updates);
+
 /* Predictor plane Qint(.,.,k) for one owned global plane k into an (8,Nx,Ny) device buffer
  * (the data a neighbouring slab needs as qint_lo / qint_hi). */
 int imhd_qint_plane(const float* Q, float* out_plane, int k, const imhd_slab* s, void* stream);
@@ -239,9 +245,9 @@ int imhd_ctx_write_grid(imhd_ctx* ctx, const char* dir);
  * between ring neighbours over NVLink (ncclSend/ncclRecv on a side stream, under the interior launch).  Every
  * imhd_ctx_* function above works on such a context and means the WHOLE domain (init_grids, the initial conditions,
  * set_state / get_state with full (8,Nz,Nx,Ny) host arrays, prime, step, stability, synchronize, imhd_run_host);
- * results are bit-identical to the single-GPU context.  Not available on it: imhd_ctx_step_granular,
- * imhd_ctx_get_grids, imhd_ctx_write_frame / write_grid (gather with imhd_ctx_get_state and call
- * imhd_h5_write_fluidvars).  NCCL is bound at run time (dlopen libnccl.so.2); single-GPU use does not need it.
+ * results are bit-identical to the single-GPU context.  imhd_ctx_write_frame gathers the slabs and writes
+ * synchronously there; imhd_ctx_step_granular and imhd_ctx_get_grids are single-GPU only.  NCCL is bound at run time
+ * (dlopen libnccl.so.2); single-GPU use does not need it.
  *   imhd_create_multi : all n_gpus slabs in THIS process, slab q on devices[q] (NULL = devices 0..n_gpus-1)
  *   imhd_create_slab  : slab `rank` of `world` in this process (one process per GPU, e.g. under torchrun);
  *                       nccl_unique_id = the 128 bytes one process obtained from imhd_nccl_unique_id. */

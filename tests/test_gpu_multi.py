@@ -83,3 +83,32 @@ def test_multi_context_initial_conditions_and_run_host(imhd, oracle_mod, O, ngpu
         assert (k0, nzl, dev) == (15, 15, 1)
         assert bits_equal(c.get_state_local(1), out2[:, k0:k0 + nzl])
     assert bits_equal(out1, out2)
+
+
+def test_driver_with_two_gpus_writes_the_same_files(tmp_path, ngpu):
+    """bin/imhd-cuda with IMHD_GPUS=2 (imhd_create_multi behind the reference's argv surface): byte-identical .h5 frames."""
+    import filecmp
+    import os
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    drv = os.path.join(ROOT, "imhd-cuda_b200", "driver")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_gpu_driver import patched_input
+
+    outs = []
+    for gpus in ("1", "2"):
+        data = str(tmp_path / f"data{gpus}") + "/"
+        os.makedirs(data)
+        inp = patched_input(tmp_path, "input_diffusion.inp", Nt=9, Nx=32, Ny=28, Nz=24)
+        env = dict(os.environ, IMHD_OUTPUT_EVERY="4", IMHD_GPUS=gpus)
+        out = subprocess.run([sys.executable, os.path.join(drv, "simulation_launcher.py"), "diffusion", "--input", inp, "--data-dir", data],
+                             capture_output=True, text=True, env=env)
+        assert out.returncode == 0, out.stdout + out.stderr
+        outs.append(data)
+    files = sorted(os.listdir(outs[0]))
+    assert files == sorted(os.listdir(outs[1])) and "fluidvars_8.h5" in files and "grid.h5" in files
+    for f in files:
+        assert filecmp.cmp(outs[0] + f, outs[1] + f, shallow=False), f
