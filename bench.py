@@ -267,6 +267,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.tolist()
 
+    if os.environ.get("IMHD_EDGE"):  # tuning hook: planes launched ahead of the interior at each slab end
+        lib.imhd_set_edge_planes(int(os.environ["IMHD_EDGE"]))
     ctx = make_ctx()
     k0, nzl, _ = ctx.slab_extent(0)
     cells_local = NX * NY * nzl
