@@ -133,7 +133,7 @@ class SlabSolver:
 
     EDGE = 8  # planes computed ahead at each slab end (>= 3: the predictor planes of the new state need them)
 
-    def __init__(self, Nx, Ny, Nz, path, D, dt, dx, dy, dz, comm=None, compute=None, device="cuda", corner_e=0.0):
+    def __init__(self, Nx, Ny, Nz, path, D, dt, dx, dy, dz, comm=None, compute=None, device="cuda", corner_e=None):
         import torch
 
         self.torch = torch
@@ -143,7 +143,10 @@ class SlabSolver:
         self.layout = SlabLayout(Nz, world, rank)
         self.Nx, self.Ny, self.Nz, self.path = Nx, Ny, Nz, path
         self.params = (D, dt, dx, dy, dz)
-        self.corner_e = corner_e
+        # path B: the wall value the column (Nx-1,Ny-1) carries at k = 0 and k = Nz-1 from step 1 on (B-8).  None = derive
+        # it from the loaded state (load_global / derive_corner_e) instead of trusting a caller-supplied number.
+        self._corner_given = corner_e is not None
+        self.corner_e = 0.0 if corner_e is None else corner_e
         if compute is None:
             from . import ops as compute
         self.compute = compute
@@ -177,6 +180,28 @@ class SlabSolver:
         lo, hi = max(L.k0 - 1, 0), min(L.k1 + 1, self.Nz)
         self.Q[self.cur][:, lo - L.k0 + 1: hi - L.k0 + 1].copy_(src[:, lo:hi])
         self.q_ready = False
+        if not self._corner_given and self.path == PATH_B:
+            self.set_corner_e(float(src[7, 0, self.Nx - 1, self.Ny - 1]))
+
+    def set_corner_e(self, e0: float):
+        """corner_e from e(Nx-1, Ny-1, k=0) of the INITIAL state: the fixed point of the reference's wall-energy map
+        (kernels_fluidbcs.cu:173).  With several ranks the owner of plane 0 (rank 0) supplies e0 to all."""
+        self.corner_e = float(self.compute.wall_energy_fixed_point(e0, self.Nx)) if hasattr(self.compute, "wall_energy_fixed_point") else 0.0
+        L = self.layout
+        D, dt, dx, dy, dz = self.params
+        self.slab = self.compute.make_slab(self.Nx, self.Ny, self.Nz, self.path, D, dt, dx, dy, dz, k0=L.k0, nzl=L.nzl, ghosts=1,
+                                           corner_e=self.corner_e)
+
+    def derive_corner_e(self):
+        """After the slabs were filled on the device (not through load_global): rank 0 reads e(Nx-1,Ny-1,0) and every
+        rank receives it."""
+        if self.path != PATH_B:
+            return
+        L = self.layout
+        e0 = float(self.Q[self.cur][7, 1, self.Nx - 1, self.Ny - 1]) if L.rank == 0 else 0.0
+        if self.comm is not None and L.world > 1:
+            e0 = self.comm.allgather_row([e0])[0][0]
+        self.set_corner_e(e0)
 
     # ---- exchanges -----------------------------------------------------------------------------------
     def exchange_qint(self, Q, qs):

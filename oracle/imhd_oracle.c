@@ -13,7 +13,7 @@
  * debug/data/rhovz/var_0.csv, pins the initial condition).  This restatement is pinned
  * against the reference ITSELF run here: oracle/_ref/libimhd_ref_cpu.so is the
  * reference's unmodified kernel sources compiled for the host (oracle/Makefile `ref`),
- * and tests/test_oracle_vs_ref.py requires BIT-EXACT agreement of every entry point
+ * and tests/test_oracle_golden.py requires BIT-EXACT agreement of every entry point
  * below with it, plus agreement with the committed fixtures under tests/golden/ that
  * were generated from it (tests/golden/make_golden.py).
  *

@@ -445,6 +445,32 @@ def test_production_size_properties(imhd, torch, O, oracle_mod):
         assert bits_equal(Q[:, k], mid), f"plane {k} lost z-invariance"
 
 
+def test_bench_workload_spacing_100_steps(imhd, torch, O, oracle_mod):
+    """The spacing bench.py runs at EVERY N (weak scaling extends z at constant dz: dx = dy = 2*3.14159/303,
+    dz = 2*3.14159/591, dt = 1e-4, D = 0.01, diffusion number dt D (2/dx^2+2/dy^2+2/dz^2) = 0.027 < 1/2) on a thin
+    box: 100 steps of the diffusion pipeline stay finite and inside 1e-5 of the oracle.  (Round 1 squeezed 592 N planes
+    into the same box: at N = 8 that is 0.57 > 1/2 and the reference's own kernels blow up at step 14.)"""
+    import importlib
+
+    om = oracle_mod
+    bench = importlib.import_module("bench")
+    dx, dy, dz = bench.spacing(bench.NZ_PER_GPU)
+    assert abs(bench.workload_config(8, "weak")["spacing"][2] - dz) < 1e-12      # constant dz at N = 8
+    assert bench.workload_config(8, "weak")["diffusion_number"] < 0.5
+    Nx, Ny, Nz = 72, 64, 20
+    bounds = (-dx * (Nx - 1) / 2, dx * (Nx - 1) / 2, -dy * (Ny - 1) / 2, dy * (Ny - 1) / 2, 0.0, dz * (Nz - 1))
+    g = O.init_grids(bounds, Nx, Ny, Nz)
+    d = tuple(float(om.grid_spacing(bounds[2 * a], bounds[2 * a + 1], n)) for a, n in enumerate((Nx, Ny, Nz)))
+    assert max(abs(a - b) / b for a, b in zip(d, (dx, dy, dz))) < 1e-5
+    Q0 = O.screwpinch_stride(1.0, *g)
+    qo, io = Q0.copy(), np.zeros_like(Q0)
+    O.prime(qo, io, om.PATH_B, D_B, DT, *d)
+    O.steps(qo, io, om.PATH_B, 100, D_B, DT, *d)
+    Q = run_fused(imhd, Q0, om.PATH_B, D_B, DT, d, 100)
+    assert np.isfinite(qo).all() and np.isfinite(Q).all()
+    assert (om.normalised_linf(Q, qo) <= 1e-5).all()
+
+
 def test_fused_path_converges_at_second_order(imhd, torch, O, oracle_mod):
     """Physics-level check of the product path through the C ABI: the advected density wave of
     tests/test_analytic_fields.py (an exact solution) converges at second order with the fused kernels too."""
