@@ -849,22 +849,26 @@ __global__ void __launch_bounds__(TI * 32, MINB) k_fused_pair(const FusedArgs A,
 // threads read the 8 consecutive columns of one i-row (one 32-byte sector).  Same device functions, same inputs
 // -> the same bits as any other variant (tests).
 // -----------------------------------------------------------------------------------------------
-constexpr int kStripCols = 8;   // staging-tile columns: the compute rows and one column either side
+constexpr int kStripCols = 12;  // staging-tile columns: three aligned 4-column groups cover the compute rows, one column either
+                                // side and the offset of the first column inside its group
 constexpr int kStripRows = 6;   // at most this many compute rows
 
-__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-
+#ifndef IMHD_STRIP_REGS
+#define IMHD_STRIP_REGS 168
+#endif
 template <int PATH>
-__global__ void __maxnreg__(168) k_fused_strip(const FusedArgs A) {
+__global__ void __maxnreg__(IMHD_STRIP_REGS) k_fused_strip(const FusedArgs A, const __grid_constant__ CUtensorMap tmap) {
     constexpr int O = Ring<PATH>::O;
     constexpr int WL = 32 - 2 * O;
-    constexpr int PITCH = kStripCols + 1;          // tile rows padded against bank conflicts
+    // The staging tile of a plane is ONE TMA box (12 columns x 32 rows x 8 variables, dense: row pitch 12 floats), four
+    // stages with an mbarrier each, filled two planes ahead.  The pitch costs 4-way bank conflicts on the ~24 tile reads
+    // per thread and plane: negligible.
+    constexpr int PITCH = kStripCols;
     constexpr int NB = 8 * 32 * PITCH;
-    extern __shared__ float strip_smem[];
-    float* sQi = strip_smem;                         // exchange of Qint(k): [2][v][tj][lane]
-    float* sN = strip_smem + 2 * 8 * kStripRows * 32;  // Q planes k+1 (neighbour reads), k+2 (own read), k+3, k+4 (in flight)
+    extern __shared__ __align__(128) float strip_smem[];
+    float* sN = strip_smem;                                            // Q planes k+1 (neighbour reads), k+2 (own read), k+3, k+4 (in flight)
+    float* sQi = strip_smem + 4 * NB;                                  // exchange of Qint(k): [2][v][tj][lane]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sQi + 2 * 8 * kStripRows * 32);  // [4]
 
     const Params& P = A.P;
     const int lane = threadIdx.x, tj = threadIdx.y, R = blockDim.y;
@@ -879,7 +883,8 @@ __global__ void __maxnreg__(168) k_fused_strip(const FusedArgs A) {
     const int oi_lo = bi == 0 ? 0 : 1 + bi * WL, oi_hi = bi == A.ntile_i - 1 ? P.Nx : 1 + (bi + 1) * WL;
     const bool owner = in_dom && i >= oi_lo && i < oi_hi && tj >= 1;  // row 0 is the predictor-only ring
     const int so = tj * 32 + lane, sjm = max(tj - 1, 0) * 32 + lane, sjp = min(tj + 1, R - 1) * 32 + lane;
-    const int st_own = lane * PITCH + tj + 1;
+    const int c0 = A.jstrip & ~3;                      // first column of the staging tile (16-byte aligned in every row)
+    const int st_own = lane * PITCH + (A.jstrip - c0) + tj + 1;
 
     const int ka = A.kfrom + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kto);
     const bool first = ka == A.ka0;
@@ -888,23 +893,24 @@ __global__ void __maxnreg__(168) k_fused_strip(const FusedArgs A) {
         const int kc = min(max(k, A.kmin), A.kmax);
         return (long long)(kc - A.kbase) * P.plane;
     };
-    const int nthr = 32 * R, t = tj * 32 + lane;
-    auto fill = [&](int k, float* buf) {  // asynchronous: plane k of the strip into a staging buffer
-        const float* src = A.Qin + plane_off(k);
-        for (int e = t; e < 32 * kStripCols; e += nthr) {
-            const int li = e >> 3, lj = e & 7;
-            const long long col = (long long)min(max(bi * WL + 1 - O + li, 0), P.Nx - 1) * P.Ny + min(A.jstrip + lj, P.Ny - 1);
-#pragma unroll
-            for (int v = 0; v < 8; ++v) cp_async4(buf + v * 32 * PITCH + li * PITCH + lj, src + v * A.vs + col);
-        }
+    const bool producer = lane == 0 && tj == 0;
+    auto fill = [&](int k, int stage) {  // producer only: plane k of the strip into a staging buffer (rows / columns outside
+                                         // the domain are zero-filled and only feed lanes whose results are discarded)
+        const int kc = min(max(k, A.kmin), A.kmax) - A.kbase;
+        mbar_expect_tx(&full[stage], NB * 4);
+        tma_load_tile(sN + stage * NB, &tmap, &full[stage], c0, bi * WL + 1 - O, kc);
     };
+    if (producer) {
+        for (int q = 0; q < 4; ++q) mbar_init(&full[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+    // stage of plane p (counted from ks + 1) is p % 4
+    if (producer)
+        for (int q = 0; q < 3; ++q) fill(ks + 1 + q, q);
 
     float q0[8], q1[8], h1[8], qim[8], qic[8];
-    fill(ks + 1, sN);
-    fill(ks + 2, sN + NB);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    fill(ks + 3, sN + 2 * NB);
-    asm volatile("cp.async.commit_group;" ::: "memory");
     ldg8(A.Qin + plane_off(ks) + lcol, 0, A.vs, q0);
     ldg8(A.Qin + plane_off(ks + 1) + lcol, 0, A.vs, q1);
     hflux(q1, h1);
@@ -923,10 +929,13 @@ __global__ void __maxnreg__(168) k_fused_strip(const FusedArgs A) {
         float* bQi = sQi + buf * 8 * kStripRows * 32;
 #pragma unroll
         for (int v = 0; v < 8; ++v) bQi[v * kStripRows * 32 + so] = qic[v];
-        asm volatile("cp.async.wait_group 1;" ::: "memory");   // plane k+2 has landed; k+3 may still be in flight
+        {   // planes k+1 and k+2 have landed?  plane p (from ks+1) is the (p/4)-th use of stage p%4
+            const int p1 = k - ks, p2 = p1 + 1;
+            if (k == ks) mbar_wait(&full[p1 & 3], 0);   // later iterations waited for it as their plane k+2
+            mbar_wait(&full[p2 & 3], (uint32_t)(p2 >> 2) & 1u);
+        }
         __syncthreads();
-        if (k + 2 < kb) fill(k + 4, sN + b4 * NB);  // two planes ahead; b4 held plane k, which nobody reads any more
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (producer && k + 2 < kb) fill(k + 4, b4);  // two planes ahead; stage b4 held plane k, which nobody reads any more
         b1 = b2;
 #pragma unroll
         for (int v = 0; v < 8; ++v) qn[v] = bN[v * 32 * PITCH + st_own];
@@ -1164,17 +1173,18 @@ extern "C" void imhd_set_kernel_variant(int flags) {
 }
 
 // 4-D view (j, i, plane, variable) of a state array for the tile loads of the TMA kernel.
-static bool make_tile_map(CUtensorMap* map, const FusedArgs& A, int nplanes, int tile_rows) {
+static bool make_tile_map(CUtensorMap* map, const FusedArgs& A, int nplanes, int tile_rows, int tile_cols = kTC,
+                          CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B) {
     const Params& P = A.P;
     PFN_cuTensorMapEncodeTiled enc = get_encode();
     if (!enc || g_force_ldg) return false;
     if (P.Ny % 4 != 0 || ((uintptr_t)A.Qin & 15) != 0) return false;  // TMA: 16-byte base and strides
     const cuuint64_t dims[4] = {(cuuint64_t)P.Ny, (cuuint64_t)P.Nx, (cuuint64_t)nplanes, 8};
     const cuuint64_t strides[3] = {(cuuint64_t)P.Ny * 4, (cuuint64_t)P.plane * 4, (cuuint64_t)A.vs * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)kTC, (cuuint32_t)tile_rows, 1, 8};
+    const cuuint32_t box[4] = {(cuuint32_t)tile_cols, (cuuint32_t)tile_rows, 1, 8};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)A.Qin, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // cudaFuncSetAttribute is per device: remember which devices already have the opt-in shared-memory size set
@@ -1287,7 +1297,7 @@ static void timing_end(TimedLaunch* t, cudaStream_t st) {
 }
 
 template <int PATH, class L>
-static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, cudaStream_t st) {
+static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, int nplanes_array, cudaStream_t st) {
     using G = typename L::G;
     const Params& P = A.P;
     const int nz = A.kto - A.kfrom;
@@ -1326,10 +1336,15 @@ static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, cudaStream_t st) {
         S.chunk = (nz + n - 1) / n;
         if (g_chunk_override > 0) S.chunk = g_chunk_override;
         S.chunk = S.chunk < 2 ? 2 : (S.chunk > nz ? nz : S.chunk);
-        constexpr size_t strip_smem = (2 * 8 * kStripRows * 32 + 4 * 8 * 32 * (kStripCols + 1)) * sizeof(float);
+        constexpr size_t strip_smem = (2 * 8 * kStripRows * 32 + 4 * 8 * 32 * kStripCols) * sizeof(float) + 64;
         static unsigned long long sdone = 0;
         if (int e = ensure_smem(k_fused_strip<PATH>, strip_smem, sdone)) return e;
-        k_fused_strip<PATH><<<dim3(S.ntile_i, 1, (nz + S.chunk - 1) / S.chunk), dim3(32, strip_rows), strip_smem, st>>>(S);
+        CUtensorMap smap;
+        // 48-byte row segments of 1216-byte rows: 64-byte L2 promotion fetches 167 MB per launch at 304x304x592 where
+        // 128-byte promotion (and, measured, "none") fetch 277 MB -- for 46 MB needed.  The kernel's duration does not
+        // depend on it (nor on cp.async vs TMA staging, nor on its register cap): see tools/experiments/README.md.
+        if (!make_tile_map(&smap, A, nplanes_array, 32, kStripCols, CU_TENSOR_MAP_L2_PROMOTION_L2_64B)) { set_error("remainder strip: tensor map"); return IMHD_E_STATE; }
+        k_fused_strip<PATH><<<dim3(S.ntile_i, 1, (nz + S.chunk - 1) / S.chunk), dim3(32, strip_rows), strip_smem, st>>>(S, smap);
         IMHD_LAUNCH_CHECK(1);
     }
     timing_end(timed, st);
@@ -1345,19 +1360,19 @@ static int launch_fused(FusedArgs& A, int nplanes_array, cudaStream_t st) {
     // kernel choice (imhd_set_kernel_variant bits 4..7): 0 = default
     switch (g_kernel) {
         case 1:
-            if (make_tile_map(&tmap, A, nplanes_array, TmaGeo<PATH, 16>::TR)) return launch_tma<PATH, OneRowLaunch<PATH, 16>>(A, tmap, st);
+            if (make_tile_map(&tmap, A, nplanes_array, TmaGeo<PATH, 16>::TR)) return launch_tma<PATH, OneRowLaunch<PATH, 16>>(A, tmap, nplanes_array, st);
             break;
         case 2:  // the 8-warp tile for either path
-            if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, PairLaunch<PATH, 8>>(A, tmap, st);
+            if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, PairLaunch<PATH, 8>>(A, tmap, nplanes_array, st);
             break;
         default:
             // Path B: 8 warps x 2 rows = a 16x32 tile, one block per SM (its two-row ring makes smaller tiles too wasteful:
             // 4-warp tiles, 2 or 3 blocks per SM, measure 30.3 / 28.2 GLUPS against 32.0).  Path A: one ring row and ~170
             // registers suffice, so three INDEPENDENT 4-warp blocks per SM (8x32 tiles, 12 warps) win: 50.6 against 44.5.
             if (PATH == IMHD_PATH_A) {
-                if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 4>::TR)) return launch_tma<PATH, PairLaunch<PATH, 4, 3>>(A, tmap, st);
+                if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 4>::TR)) return launch_tma<PATH, PairLaunch<PATH, 4, 3>>(A, tmap, nplanes_array, st);
             } else {
-                if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, PairLaunch<PATH, 8>>(A, tmap, st);
+                if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, PairLaunch<PATH, 8>>(A, tmap, nplanes_array, st);
             }
             break;
     }
