@@ -96,6 +96,7 @@ SIGNATURES = {
     "imhd_ctx_set_state_local": (_i, [_p, _i, _p]),
     "imhd_ctx_get_state_local": (_i, [_p, _i, _p]),
     "imhd_set_edge_planes": (None, [_i]),
+    "imhd_stability_mode": (None, [_i]),
     "imhd_fused_timing": (None, [_i]),
     "imhd_fused_timing_read": (_i, [C.POINTER(C.c_double), C.POINTER(_i), C.POINTER(C.c_longlong)]),
 }

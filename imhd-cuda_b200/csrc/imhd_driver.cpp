@@ -10,6 +10,7 @@
 // Optional environment: IMHD_OUTPUT_EVERY=n (default 1 = the reference's behaviour), IMHD_DEVICE=d, IMHD_GPUS=N (the
 // domain as N z-slabs on devices 0..N-1 of this box, exchanged over NVLink: imhd_create_multi; output is then gathered
 // and written synchronously),
+// IMHD_STABILITY_QUIRKS=1 makes the CFL report use the reference's own (slipped) y / z Jacobians,
 // IMHD_IC=<registry key>[:p0[,p1]] selects the initial condition by the reference's registry key
 // (include/on-device/utils/configurers.hpp:21-29) instead of the one each shipped driver hard-codes; parameters left
 // out come from argv (J0, r_max_coeff, A, k_harmonic) where the argv list has them.
@@ -100,6 +101,7 @@ int main(int argc, char* argv[]) {
     if (eigen_bin_name != "none") {
         // the reference forks its host scanner here (no_diffusion.cu:259-276, compute_stability.cpp); same report, on the device
         imhd_stability st;
+        if (getenv("IMHD_STABILITY_QUIRKS")) imhd_stability_mode(IMHD_STABILITY_REFERENCE_QUIRKS);  // the reference's own y / z matrices (B-26)
         CHECK(imhd_ctx_stability(ctx, dt, &st));
         printf("Old timestep: %g\nLargest violation: %g at (i,j,k) = (%d,%d,%d)\nNew timestep: %g\n"
                "Total number of stability violations detected: %llu\n",

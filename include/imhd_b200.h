@@ -151,6 +151,15 @@ typedef struct imhd_stability {
     float dt_new;                  /* 0.1 * dt / max_lhs: the reference's proposal (:139-141); 0 if max_lhs == 0 */
 } imhd_stability;
 int imhd_stability_scan(const float* Q, const imhd_slab* s, imhd_stability* host_out, void* stream);
+/* Which spectra the scan uses (process-wide; default IMHD_STABILITY_WAVE_SPEEDS):
+ *   IMHD_STABILITY_WAVE_SPEEDS       the exact ideal-MHD wave speeds in x, y and z (closed form);
+ *   IMHD_STABILITY_REFERENCE_QUIRKS  the reference's own report: closed form for its x matrix (which has exactly the wave
+ *                                    spectrum) and the spectral radius of ITS y and z matrices, transcription slips
+ *                                    included (computeB / computeC, compute_stability.cpp:296-459), eigenvalues by
+ *                                    Hessenberg reduction + shifted QR per cell on the device in place of Eigen (:165-181). */
+#define IMHD_STABILITY_WAVE_SPEEDS 0
+#define IMHD_STABILITY_REFERENCE_QUIRKS 1
+void imhd_stability_mode(int mode);
 
 /* e <- p(e,0,0)/(gamma-1) iterated to its fixed point (lib/on-device/kernels_fluidbcs.cu:173,187; every
  * x-thread of the reference launch re-applies it).  Scalar host helper, identity when e == 0. */

@@ -134,6 +134,14 @@ def wave_speed_lhs(Q, dt, dx, dy, dz):
     return dt / dx * lam[..., 0] + dt / dy * lam[..., 1] + dt / dz * lam[..., 2]
 
 
+def reference_lhs(Q, dt, dx, dy, dz):
+    """LHS field (Nz, Nx, Ny) exactly as the reference forms it (:157-181): max |eigenvalue| of ITS A, B, C (slips
+    included) per cell -- what the library's IMHD_STABILITY_REFERENCE_QUIRKS mode reports."""
+    U = np.moveaxis(np.asarray(Q, np.float32), 0, -1)
+    lam = spectral_radii(U).astype(np.float64)
+    return dt / dx * lam[..., 0] + dt / dy * lam[..., 1] + dt / dz * lam[..., 2]
+
+
 def scan(lhs, dt, alpha=0.1):
     """The scanner's summary (:112-141): number of cells with LHS >= 1, the largest LHS and its (i, j, k), the
     proposed dt = alpha * dt / max LHS.  `lhs` has shape (Nz, Nx, Ny); NaN cells (rho = 0) are ignored, as a NaN

@@ -120,6 +120,41 @@ def test_cuda_scan_matches_the_closed_form(imhd, torch, O, oracle_mod, dims):
 
 
 @pytest.mark.gpu
+def test_cuda_scan_reference_quirks_mode(imhd, torch, O, oracle_mod):
+    """IMHD_STABILITY_REFERENCE_QUIRKS: the spectral radii of the reference's OWN y and z matrices (slips B-26 included),
+    Hessenberg + shifted QR per cell on the device, against the numpy restatement's LAPACK eigenvalues of the same
+    matrices; the default mode keeps reporting the exact wave speeds."""
+    ops = imhd.ops
+    lib = imhd._lib.load()
+    dims = (14, 12, 9)
+    Nx, Ny, Nz = dims
+    _, d, Q0 = make_case(O, oracle_mod, *dims, ic="bennett")
+    U = physical_states(Nx * Ny * Nz, seed=4).reshape(Nz, Nx, Ny, 8)
+    Qr = np.ascontiguousarray(np.moveaxis(U, -1, 0))
+    try:
+        lib.imhd_stability_mode(1)
+        for Q, dt in ((Qr, 0.01), (Qr, 0.05), (Q0, 0.02)):
+            slab = ops.make_slab(Nx, Ny, Nz, 0, 0.0, dt, *d)
+            got = ops.stability_scan(torch.from_numpy(Q).cuda(), slab)
+            lhs = st.reference_lhs(Q, dt, *d)
+            want = st.scan(lhs, dt)
+            assert got["max_lhs"] == pytest.approx(want["max_lhs"], rel=2e-4)   # fp32 LAPACK vs fp64 QR on fp32 matrices
+            k, i, j = want["argmax_ijk"][2], want["argmax_ijk"][0], want["argmax_ijk"][1]
+            gi, gj, gk = got["argmax_ijk"]
+            assert lhs[gk, gi, gj] == pytest.approx(lhs[k, i, j], rel=2e-4)
+            near = int((np.abs(np.nan_to_num(lhs, nan=0.0) - 1.0) < 5e-4).sum())
+            assert abs(got["violations"] - want["violations"]) <= near
+        # the slipped matrices do NOT have the wave spectrum: the two modes differ on generic states
+        quirk = got["max_lhs"]
+        lib.imhd_stability_mode(0)
+        exact = ops.stability_scan(torch.from_numpy(Q0).cuda(), ops.make_slab(Nx, Ny, Nz, 0, 0.0, 0.02, *d))["max_lhs"]
+        assert exact == pytest.approx(st.scan(st.wave_speed_lhs(Q0, 0.02, *d), 0.02)["max_lhs"], rel=2e-6)
+        assert quirk != exact
+    finally:
+        lib.imhd_stability_mode(0)
+
+
+@pytest.mark.gpu
 def test_cuda_scan_edge_cases(imhd, torch, O, oracle_mod):
     ops = imhd.ops
     dims = (12, 8, 6)

@@ -34,5 +34,16 @@ try:
 except Exception:
     pass
 gbs = cells * 32 / ms * 1e-6
-print(json.dumps({"workload": "304x304x592 screw pinch", "scan": r, "ms_per_scan_incl_sync_and_d2h": ms,
-                  "algorithmic_GBps": gbs, "hbm_peak_GBps": peak, "frac": gbs / peak}))
+print(json.dumps({"workload": "304x304x592 screw pinch", "mode": "wave speeds (closed form)", "scan": r,
+                  "ms_per_scan_incl_sync_and_d2h": ms, "algorithmic_GBps": gbs, "hbm_peak_GBps": peak, "frac": gbs / peak}))
+# the reference's report: closed form in x, the spectral radius of ITS y and z matrices by QR per cell
+imhd._lib.load().imhd_stability_mode(1)
+r = ops.stability_scan(Q, slab)
+e0.record()
+for _ in range(3):
+    r = ops.stability_scan(Q, slab)
+e1.record()
+torch.cuda.synchronize()
+imhd._lib.load().imhd_stability_mode(0)
+print(json.dumps({"workload": "304x304x592 screw pinch", "mode": "reference-quirks (two 8x8 eigenproblems per cell, fp64 QR)",
+                  "scan": r, "ms_per_scan_incl_sync_and_d2h": e0.elapsed_time(e1) / 3}))
