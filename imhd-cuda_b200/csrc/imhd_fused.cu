@@ -839,6 +839,461 @@ __global__ void __launch_bounds__(TI * 32, MINB) k_fused_pair(const FusedArgs A,
     }
 }
 
+// Split-phase variant of k_fused_pair: the block-wide __syncthreads per plane becomes an mbarrier pair (arrive right after
+// a warp has published its rows of Qint(k+1), wait right before it reads its neighbours' rows of Qint(k) one iteration
+// later), with four exchange buffers so that a warp may run up to one plane ahead of the slowest one.
+template <int PATH, int TI>
+struct SplitGeo : PairGeo<PATH, TI> {
+    using B = PairGeo<PATH, TI>;
+    static constexpr int NXBUF = 4;
+    static constexpr size_t SMEM = B::NSTAGE * B::STAGE_BYTES + NXBUF * B::XBUF * 4 + 64;
+};
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int PATH, int TI, int MINB = 1>
+__global__ void __launch_bounds__(TI * 32, MINB) k_fused_split(const FusedArgs A, const __grid_constant__ CUtensorMap tmap) {
+    using G = SplitGeo<PATH, TI>;
+    constexpr int NS = G::NSTAGE;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* tiles = reinterpret_cast<float*>(smem_raw);                       // [NS][8][TR][kTC]
+    float* xch = tiles + NS * G::STAGE_FLOATS;                                // [2][first,last][8][TI][32]  Qint exchange
+    uint64_t* full = reinterpret_cast<uint64_t*>(xch + G::NXBUF * G::XBUF);   // [NS] tile landed
+    uint64_t* xbar = full + NS;                                               // [2] Qint rows of a plane published (even / odd planes)
+
+    const Params& P = A.P;
+    const int lane = threadIdx.x, ti = threadIdx.y;
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    const int ib = bi * G::WI, jb = bj * G::WJ;
+    const int t0 = ti * 2, i0 = ib + t0, j = jb + lane;
+    const int oi_lo = bi == 0 ? 0 : ib + 1, oi_hi = bi == A.ntile_i - 1 ? P.Nx : ib + G::WI + 1;
+    const int oj_lo = bj == 0 ? 0 : jb + 1, oj_hi = bj == A.ntile_j - 1 ? P.Ny : jb + G::WJ + 1;
+    PairThread T;
+    T.rows = 0;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int i = i0 + rr, t = t0 + rr;
+        const bool corr_row = t >= 1 && (PATH == IMHD_PATH_A || t <= G::NR - 2);  // rows with valid Qint neighbours
+        if (i == P.Nx - 1) T.rows |= 1u << rr;
+        if (i > 0 && i < P.Nx - 1) T.rows |= 1u << (8 + rr);
+        if (corr_row && i > 0 && (PATH == IMHD_PATH_A ? i < P.Nx : i < P.Nx - 1)) T.rows |= 1u << (16 + rr);
+        if (i < P.Nx && i >= oi_lo && i < oi_hi) T.rows |= 1u << (24 + rr);
+    }
+    const bool interior_j = j > 0 && j < P.Ny - 1;
+    T.lanes = (j == P.Ny - 1 ? 1u : 0u) | (interior_j ? 2u : 0u) |
+              ((PATH == IMHD_PATH_A ? (j > 0 && j < P.Ny) : interior_j) ? 4u : 0u) | ((j < P.Ny && j >= oj_lo && j < oj_hi) ? 8u : 0u);
+    // the box starts at the 4-column boundary at or below jb-1 (measured: a misaligned inner coordinate traps)
+    const int c0 = ((jb - 1 + 4) / 4) * 4 - 4;
+    T.own = (t0 + 1) * kTC + (jb - 1 - c0) + lane + 1;
+    T.xs = ti * 32 + lane;
+    T.xsm = max(ti - 1, 0) * 32 + lane;
+    T.xsp = min(ti + 1, TI - 1) * 32 + lane;
+    T.i0 = i0;
+    T.jc = min(j, P.Ny - 1);
+    keep(T.rows); keep(T.lanes); keep(T.own); keep(T.xs); keep(T.xsm); keep(T.xsp);
+
+    const int ka = A.kfrom + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kto);
+    const bool first = ka == A.ka0;  // the plane below is the slab's qint_lo; otherwise re-derive it in a warm-up plane
+    const int ks = first ? ka - 1 : ka - 2;
+    const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
+    const int klast = kb + 1;  // last plane any iteration reads
+
+    auto issue = [&](int plane, int stage) {  // producer only
+        const int kc = min(max(plane, A.kmin), A.kmax) - A.kbase;
+        mbar_expect_tx(&full[stage], G::STAGE_BYTES);
+        tma_load_tile(tiles + stage * G::STAGE_FLOATS, &tmap, &full[stage], c0, ib - 1, kc);
+    };
+
+    if (producer) {
+        for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+        mbar_init(&xbar[0], TI * 32);
+        mbar_init(&xbar[1], TI * 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+    if (producer)
+        for (int s = 0; s < NS; ++s) issue(ks + s, s);
+
+    float2 qa[8], qb[8], qc[8], hb[8], hc[8], ia[8], ib_[8], ic[8];
+    PrimT<float2> pb, pc;
+    constexpr int VS = G::TR * kTC;
+    mbar_wait(&full[0], 0);
+    mbar_wait(&full[1], 0);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        qa[v] = make_float2(tiles[v * VS + T.own], tiles[v * VS + T.own + kTC]);
+        qb[v] = make_float2(tiles[G::STAGE_FLOATS + v * VS + T.own], tiles[G::STAGE_FLOATS + v * VS + T.own + kTC]);
+        ia[v] = make_float2(1.0f, 1.0f);
+        ib_[v] = make_float2(1.0f, 1.0f);
+    }
+    pb = make_prim(qb);
+    flux_idx<DIR_Z>(qb, pb, hb);
+    if (first) {  // Qint(ka-1); rows beyond the domain read the last row (they never produce output)
+        float a[8], b[8];
+        ldg8(A.qlo, (long long)min(i0, P.Nx - 1) * P.Ny + T.jc, P.plane, a);
+        ldg8(A.qlo, (long long)min(i0 + 1, P.Nx - 1) * P.Ny + T.jc, P.plane, b);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) ib_[v] = make_float2(a[v], b[v]);
+    }
+
+    // output pointer of the first row at plane ks; stores are predicated off below plane ka
+    float* outp = A.Qout + (long long)(ks - A.kbase) * P.plane + (long long)i0 * P.Ny + T.jc;
+    int xr = 0;          // exchange buffer of this plane (index): plane ks+it reads buffer it & 3 and writes (it+1) & 3
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        xch[v * TI * 32 + T.xs] = ib_[v].x;
+        xch[(8 + v) * TI * 32 + T.xs] = ib_[v].y;
+    }
+    mbar_arrive(&xbar[0]);
+    int s2 = 2;          // stage of plane k+2
+    uint32_t par = 0x3;  // bit s = parity of the next wait on stage s: stages 0,1 were waited once in the prologue
+    uint32_t xpar = 0;   // bit b = parity of the next wait on xbar[b]
+#pragma unroll 1
+    for (int k = ks; k < kb; ++k) {
+        const int s1 = (s2 + NS - 1) % NS, s0 = (s2 + NS - 2) % NS;
+        const float* xq = xch + xr * G::XBUF;   // Qint(k) rows, stored during the previous iteration
+        const int xb = xr & 1;
+        xr = (xr + 1) & 3;
+        mbar_wait(&full[s2], (par >> s2) & 1u);
+        par ^= 1u << s2;
+        pair_predict<PATH, TI>(A, T, k + 1 == A.hi_plane, tiles + s1 * G::STAGE_FLOATS, tiles + s2 * G::STAGE_FLOATS, qa, qb, qc, hb, hc,
+                               pb, pc, ic);
+        {   // publish the rows of Qint(k+1) for the next plane and say so (release): that buffer last held Qint(k-3), read in
+            // iteration k-3, and every warp has been seen in iteration k-2 (its arrival for Qint(k-1), which this warp waited on
+            // one iteration ago)
+            float* xn = xch + xr * G::XBUF;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                xn[v * TI * 32 + T.xs] = ic[v].x;
+                xn[(8 + v) * TI * 32 + T.xs] = ic[v].y;
+            }
+            mbar_arrive(&xbar[xb ^ 1]);
+        }
+        // the neighbours' rows of Qint(k): published during their iteration k-1 -- normally long ago, so the warps of a block
+        // drift apart by up to half a plane instead of meeting at a block-wide barrier every plane
+        mbar_wait(&xbar[xb], (xpar >> xb) & 1u);
+        xpar ^= 1u << xb;
+        // every warp has finished the predictor of iteration k-1, the last reader of the tile of plane k: refill its stage
+        if (producer && k + NS <= klast) issue(k + NS, s0);
+        pair_correct<PATH, TI>(A, T, k >= ka, xq, qa, ia, ib_, ic, outp);
+        outp += P.plane;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            qa[v] = qb[v]; qb[v] = qc[v]; hb[v] = hc[v];
+            ia[v] = ib_[v]; ib_[v] = ic[v];
+        }
+        pb = pc;
+        s2 = (s2 + 1) % NS;
+    }
+}
+
+// -----------------------------------------------------------------------------------------------
+// The register-tiled kernel with CARRIED FLUXES (path B hot path).  Same march, tiles, Qint exchange and corrector as
+// k_fused_pair; what changes is where the predictor's fluxes come from.  k_fused_pair evaluates, per thread and plane,
+// F, G of its own two rows AND G of the column to the right (packed) AND F of the row below (scalar) -- the last two
+// are values the neighbouring lane / thread row evaluates as its own.  Here every thread evaluates F, G, H of its own
+// two rows ONCE, when the plane is first read (Q(k+2) in iteration k), carries them in the register queue (15
+// non-trivial components instead of H and the primitives) and publishes G of both rows and F of its first row to
+// shared memory for the iteration after; the one row below and the one column right of the thread tile, which no
+// thread owns, are evaluated by one designated warp each (scalar, 16 / 32 cells) one plane ahead as well.  A
+// neighbour's flux is the same function of the same tile values wherever it is evaluated -> the same bits as
+// k_fused_pair (tests).  Per warp and plane that removes 93 fp32-pipe cycles of 866 for 18 STS + 18 LDS.
+// -----------------------------------------------------------------------------------------------
+template <class V>
+struct FluxQ {   // F, G, H (indexed family) of one state, non-trivial components only:
+    V f[6];      //   F: MX MY MZ BY BZ EN          (F[RHO] = Q[MX], F[BX] = 0)
+    V g[5];      //   G: MY MZ BX BZ EN             (G[RHO] = Q[MY], G[BY] = 0, G[MX] = F[MY])
+    V h[4];      //   H: MZ BX BY EN                (H[RHO] = Q[MZ], H[BZ] = 0, H[MX] = F[MZ], H[MY] = G[MZ])
+};
+
+template <class V>
+__device__ __forceinline__ void flux_all(const V U[8], FluxQ<V>& X) {
+    const PrimT<V> s = make_prim(U);
+    V f[8], g[8], h[8];
+    flux_idx<DIR_X>(U, s, f);
+    flux_idx<DIR_Y>(U, s, g);
+    flux_idx<DIR_Z>(U, s, h);
+    X.f[0] = f[MX]; X.f[1] = f[MY]; X.f[2] = f[MZ]; X.f[3] = f[BY]; X.f[4] = f[BZ]; X.f[5] = f[EN];
+    X.g[0] = g[MY]; X.g[1] = g[MZ]; X.g[2] = g[BX]; X.g[3] = g[BZ]; X.g[4] = g[EN];
+    X.h[0] = h[MZ]; X.h[1] = h[BX]; X.h[2] = h[BY]; X.h[3] = h[EN];
+}
+template <class V>
+__device__ __forceinline__ void flux_expand(const V U[8], const FluxQ<V>& X, V f[8], V g[8], V h[8]) {
+    f[RHO] = U[MX]; f[MX] = X.f[0]; f[MY] = X.f[1]; f[MZ] = X.f[2]; f[BX] = vset<V>(0.0f); f[BY] = X.f[3]; f[BZ] = X.f[4]; f[EN] = X.f[5];
+    g[RHO] = U[MY]; g[MX] = X.f[1]; g[MY] = X.g[0]; g[MZ] = X.g[1]; g[BX] = X.g[2]; g[BY] = vset<V>(0.0f); g[BZ] = X.g[3]; g[EN] = X.g[4];
+    h[RHO] = U[MZ]; h[MX] = X.f[2]; h[MY] = X.g[1]; h[MZ] = X.h[0]; h[BX] = X.h[1]; h[BY] = X.h[2]; h[BZ] = vset<V>(0.0f); h[EN] = X.h[3];
+}
+
+template <int PATH, int TI>
+struct CarryGeo : PairGeo<PATH, TI> {
+    using B = PairGeo<PATH, TI>;
+    static constexpr int FXV = (TI + 1) * 32;        // component stride of the published x fluxes: thread rows 0..TI-1 (their
+                                                     // first row) + slot TI = the row below the thread tile
+    static constexpr int FXBUF = 6 * FXV;
+    static constexpr int GYP = 33;                   // row pitch of the published y fluxes: 32 lanes + the column right of the tile
+    static constexpr int GYV = B::NR * GYP;
+    static constexpr int GYBUF = 6 * GYV;
+    static constexpr size_t SMEM = B::NSTAGE * B::STAGE_BYTES + (B::NXBUF * B::XBUF + 2 * FXBUF + 2 * GYBUF) * 4 + 64;
+};
+
+// Fluxes of plane k+2 (tile tq2) -> registers (Xn) and the NEXT plane's exchange buffers (fxn, gyn); predictor of plane
+// k+1 from the carried fluxes X1 and THIS plane's exchange buffers (fxc, gyc), which were filled one iteration ago.
+template <int PATH, int TI>
+__device__ __forceinline__ void carry_predict(const FusedArgs& A, const PairThread& T, int role, int gcol, bool hi, const float* tq1,
+                                              const float* tq2, const float* fxc, const float* gyc, float* fxn, float* gyn,
+                                              const float2 (&q0)[8], const float2 (&q1)[8], float2 (&qn)[8],
+                                              const FluxQ<float2>& X1, FluxQ<float2>& Xn, float2 (&qip)[8]) {
+    using G = CarryGeo<PATH, TI>;
+    const Params& P = A.P;
+    constexpr int VS = G::TR * kTC;   // variable stride inside a tile
+    const FlagT<float2> right = {T.right(), T.right()};
+    const int lane = T.xs & 31, ti = T.xs >> 5;
+    // this plane's neighbour values first: their latency hides under the flux evaluation below
+    float xlast[8], xfirst[8], fl[8];
+    float2 yp[8], ym[8], gy[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        xlast[v] = tq1[v * VS + T.own + 2 * kTC];                       // Q(k+1) one row below the thread's rows
+        yp[v] = make_float2(tq1[v * VS + T.own + 1], tq1[v * VS + T.own + kTC + 1]);
+        if (PATH == IMHD_PATH_B) {
+            xfirst[v] = tq1[v * VS + T.own - kTC];                      // ... and one row above
+            ym[v] = make_float2(tq1[v * VS + T.own - 1], tq1[v * VS + T.own + kTC - 1]);
+        }
+    }
+    {   // F(Q(k+1)) of the row below (the first row of the next thread row, or slot TI) and G(Q(k+1)) one column right
+        const float* fp = fxc + (ti + 1) * 32 + lane;
+        const float* gp = gyc + (2 * ti) * G::GYP + lane + 1;
+        fl[RHO] = xlast[MX]; fl[BX] = 0.0f;
+        fl[MX] = fp[0 * G::FXV]; fl[MY] = fp[1 * G::FXV]; fl[MZ] = fp[2 * G::FXV];
+        fl[BY] = fp[3 * G::FXV]; fl[BZ] = fp[4 * G::FXV]; fl[EN] = fp[5 * G::FXV];
+        gy[RHO] = make_float2(yp[MY].x, yp[MY].y); gy[BY] = make_float2(0.0f, 0.0f);
+        gy[MX] = make_float2(gp[0 * G::GYV], gp[0 * G::GYV + G::GYP]);
+        gy[MY] = make_float2(gp[1 * G::GYV], gp[1 * G::GYV + G::GYP]);
+        gy[MZ] = make_float2(gp[2 * G::GYV], gp[2 * G::GYV + G::GYP]);
+        gy[BX] = make_float2(gp[3 * G::GYV], gp[3 * G::GYV + G::GYP]);
+        gy[BZ] = make_float2(gp[4 * G::GYV], gp[4 * G::GYV + G::GYP]);
+        gy[EN] = make_float2(gp[5 * G::GYV], gp[5 * G::GYV + G::GYP]);
+    }
+    // ---- plane k+2: own state, its fluxes, and what the neighbours will want of them next iteration ----------------
+#pragma unroll
+    for (int v = 0; v < 8; ++v) qn[v] = make_float2(tq2[v * VS + T.own], tq2[v * VS + T.own + kTC]);
+    flux_all(qn, Xn);
+    {
+        float* fp = fxn + ti * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) fp[c * G::FXV] = Xn.f[c].x;
+        float* gp = gyn + (2 * ti) * G::GYP + lane;
+        gp[0 * G::GYV] = Xn.f[1].x; gp[0 * G::GYV + G::GYP] = Xn.f[1].y;          // G[MX] = F[MY]
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { gp[(c + 1) * G::GYV] = Xn.g[c].x; gp[(c + 1) * G::GYV + G::GYP] = Xn.g[c].y; }
+    }
+    if (role) {  // warp-uniform: the last warp owns the row below the thread tile, warp 0 the column to its right
+        float u[8], t[8];
+        const int off = role == 1 ? T.own + 2 * kTC : gcol;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) u[v] = tq2[v * VS + off];
+        const Prim s = make_prim(u);
+        if (role == 1) {
+            flux_idx<DIR_X>(u, s, t);
+            float* fp = fxn + TI * 32 + lane;
+            fp[0 * G::FXV] = t[MX]; fp[1 * G::FXV] = t[MY]; fp[2 * G::FXV] = t[MZ];
+            fp[3 * G::FXV] = t[BY]; fp[4 * G::FXV] = t[BZ]; fp[5 * G::FXV] = t[EN];
+        } else {
+            flux_idx<DIR_Y>(u, s, t);
+            float* gp = gyn + (lane & (G::NR - 1)) * G::GYP + 32;   // lanes >= NR repeat rows 0.. with the same values
+            gp[0 * G::GYV] = t[MX]; gp[1 * G::GYV] = t[MY]; gp[2 * G::GYV] = t[MZ];
+            gp[3 * G::GYV] = t[BX]; gp[4 * G::GYV] = t[BZ]; gp[5 * G::GYV] = t[EN];
+        }
+    }
+    // ---- predictor of plane k+1 -----------------------------------------------------------------------------
+    {
+        float2 f[8], g[8], h1[8], hn[8], dF[8], xsum[8];
+        {
+            float2 fdum[8], gdum[8];
+            flux_expand(q1, X1, f, g, h1);
+            flux_expand(qn, Xn, fdum, gdum, hn);
+        }
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            dF[v].x = T.bottom(0) ? -f[v].x : f[v].y - f[v].x;   // the second row's flux is the first row's i+1 neighbour
+            dF[v].y = T.bottom(1) ? -f[v].y : fl[v] - f[v].y;
+            if (PATH == IMHD_PATH_B) xsum[v] = make_float2(q1[v].y + xfirst[v], xlast[v] + q1[v].x);
+        }
+        qint_combine<PATH, float2>(q1, dF, g, gy, h1, hn, xsum, ym, yp, q0, qn, {T.bottom(0), T.bottom(1)}, right,
+                                   {T.interior_i(0) && T.interior_j(), T.interior_i(1) && T.interior_j()}, P, qip);
+    }
+    if (__builtin_expect(hi, 0)) {  // the plane above the slab comes from the neighbour (or is the periodic image): once per slab
+        float a[8], b[8];
+        ldg8(A.qhi, (long long)min(T.i0, P.Nx - 1) * P.Ny + T.jc, P.plane, a);
+        ldg8(A.qhi, (long long)min(T.i0 + 1, P.Nx - 1) * P.Ny + T.jc, P.plane, b);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) qip[v] = make_float2(a[v], b[v]);
+    }
+}
+
+template <int PATH, int TI, int MINB = 1>
+__global__ void __launch_bounds__(TI * 32, MINB) k_fused_carry(const FusedArgs A, const __grid_constant__ CUtensorMap tmap) {
+    using G = CarryGeo<PATH, TI>;
+    constexpr int NS = G::NSTAGE;
+    static_assert(G::NR <= 32 && (G::NR & (G::NR - 1)) == 0, "the column right of the tile is evaluated by the lanes of one warp");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* tiles = reinterpret_cast<float*>(smem_raw);                       // [NS][8][TR][kTC]
+    float* xch = tiles + NS * G::STAGE_FLOATS;                                // [2][first,last][8][TI][32]  Qint exchange
+    float* fxb = xch + G::NXBUF * G::XBUF;                                    // [2][6][TI+1][32]  F(Q), first rows + the row below the tile
+    float* gyb = fxb + 2 * G::FXBUF;                                          // [2][6][NR][33]    G(Q), all rows + the column right of the tile
+    uint64_t* full = reinterpret_cast<uint64_t*>(gyb + 2 * G::GYBUF);         // [NS] tile landed
+
+    const Params& P = A.P;
+    const int lane = threadIdx.x, ti = threadIdx.y;
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    const int ib = bi * G::WI, jb = bj * G::WJ;
+    const int t0 = ti * 2, i0 = ib + t0, j = jb + lane;
+    const int oi_lo = bi == 0 ? 0 : ib + 1, oi_hi = bi == A.ntile_i - 1 ? P.Nx : ib + G::WI + 1;
+    const int oj_lo = bj == 0 ? 0 : jb + 1, oj_hi = bj == A.ntile_j - 1 ? P.Ny : jb + G::WJ + 1;
+    PairThread T;
+    T.rows = 0;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int i = i0 + rr, t = t0 + rr;
+        const bool corr_row = t >= 1 && (PATH == IMHD_PATH_A || t <= G::NR - 2);  // rows with valid Qint neighbours
+        if (i == P.Nx - 1) T.rows |= 1u << rr;
+        if (i > 0 && i < P.Nx - 1) T.rows |= 1u << (8 + rr);
+        if (corr_row && i > 0 && (PATH == IMHD_PATH_A ? i < P.Nx : i < P.Nx - 1)) T.rows |= 1u << (16 + rr);
+        if (i < P.Nx && i >= oi_lo && i < oi_hi) T.rows |= 1u << (24 + rr);
+    }
+    const bool interior_j = j > 0 && j < P.Ny - 1;
+    T.lanes = (j == P.Ny - 1 ? 1u : 0u) | (interior_j ? 2u : 0u) |
+              ((PATH == IMHD_PATH_A ? (j > 0 && j < P.Ny) : interior_j) ? 4u : 0u) | ((j < P.Ny && j >= oj_lo && j < oj_hi) ? 8u : 0u);
+    // the box starts at the 4-column boundary at or below jb-1 (measured: a misaligned inner coordinate traps)
+    const int c0 = ((jb - 1 + 4) / 4) * 4 - 4;
+    T.own = (t0 + 1) * kTC + (jb - 1 - c0) + lane + 1;
+    T.xs = ti * 32 + lane;
+    T.xsm = max(ti - 1, 0) * 32 + lane;
+    T.xsp = min(ti + 1, TI - 1) * 32 + lane;
+    T.i0 = i0;
+    T.jc = min(j, P.Ny - 1);
+    int role = ti == TI - 1 ? 1 : (ti == 0 ? 2 : 0);
+    int gcol = ((lane & (G::NR - 1)) + 1) * kTC + (jb - 1 - c0) + 33;   // tile offset of (thread-tile row lane, the column right of the tile)
+    keep(T.rows); keep(T.lanes); keep(T.own); keep(T.xs); keep(T.xsm); keep(T.xsp); keep(role); keep(gcol);
+
+    const int ka = A.kfrom + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kto);
+    const bool first = ka == A.ka0;  // the plane below is the slab's qint_lo; otherwise re-derive it in a warm-up plane
+    const int ks = first ? ka - 1 : ka - 2;
+    const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
+    const int klast = kb + 1;  // last plane any iteration reads
+
+    auto issue = [&](int plane, int stage) {  // producer only
+        const int kc = min(max(plane, A.kmin), A.kmax) - A.kbase;
+        mbar_expect_tx(&full[stage], G::STAGE_BYTES);
+        tma_load_tile(tiles + stage * G::STAGE_FLOATS, &tmap, &full[stage], c0, ib - 1, kc);
+    };
+
+    if (producer) {
+        for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+    if (producer)
+        for (int s = 0; s < NS; ++s) issue(ks + s, s);
+
+    float2 qa[8], qb[8], qc[8], ia[8], ib_[8], ic[8];
+    FluxQ<float2> Xb, Xc;
+    constexpr int VS = G::TR * kTC;
+    mbar_wait(&full[0], 0);
+    mbar_wait(&full[1], 0);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        qa[v] = make_float2(tiles[v * VS + T.own], tiles[v * VS + T.own + kTC]);
+        qb[v] = make_float2(tiles[G::STAGE_FLOATS + v * VS + T.own], tiles[G::STAGE_FLOATS + v * VS + T.own + kTC]);
+        ia[v] = make_float2(1.0f, 1.0f);
+        ib_[v] = make_float2(1.0f, 1.0f);
+    }
+    if (first) {  // Qint(ka-1); rows beyond the domain read the last row (they never produce output)
+        float a[8], b[8];
+        ldg8(A.qlo, (long long)min(i0, P.Nx - 1) * P.Ny + T.jc, P.plane, a);
+        ldg8(A.qlo, (long long)min(i0 + 1, P.Nx - 1) * P.Ny + T.jc, P.plane, b);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) ib_[v] = make_float2(a[v], b[v]);
+    }
+    {   // fluxes of plane ks+1 and their exchange entries, as the loop body produces them for every later plane
+        const float* tq = tiles + G::STAGE_FLOATS;
+        flux_all(qb, Xb);
+        float* fp = fxb + ti * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) fp[c * G::FXV] = Xb.f[c].x;
+        float* gp = gyb + (2 * ti) * G::GYP + lane;
+        gp[0 * G::GYV] = Xb.f[1].x; gp[0 * G::GYV + G::GYP] = Xb.f[1].y;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { gp[(c + 1) * G::GYV] = Xb.g[c].x; gp[(c + 1) * G::GYV + G::GYP] = Xb.g[c].y; }
+        if (role) {
+            float u[8], t[8];
+            const int off = role == 1 ? T.own + 2 * kTC : gcol;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) u[v] = tq[v * VS + off];
+            const Prim s = make_prim(u);
+            if (role == 1) {
+                flux_idx<DIR_X>(u, s, t);
+                float* fq = fxb + TI * 32 + lane;
+                fq[0 * G::FXV] = t[MX]; fq[1 * G::FXV] = t[MY]; fq[2 * G::FXV] = t[MZ];
+                fq[3 * G::FXV] = t[BY]; fq[4 * G::FXV] = t[BZ]; fq[5 * G::FXV] = t[EN];
+            } else {
+                flux_idx<DIR_Y>(u, s, t);
+                float* gq = gyb + (lane & (G::NR - 1)) * G::GYP + 32;
+                gq[0 * G::GYV] = t[MX]; gq[1 * G::GYV] = t[MY]; gq[2 * G::GYV] = t[MZ];
+                gq[3 * G::GYV] = t[BX]; gq[4 * G::GYV] = t[BZ]; gq[5 * G::GYV] = t[EN];
+            }
+        }
+    }
+
+    // output pointer of the first row at plane ks; stores are predicated off below plane ka
+    float* outp = A.Qout + (long long)(ks - A.kbase) * P.plane + (long long)i0 * P.Ny + T.jc;
+    int xsel = 0, fsel = 0, gsel = 0;   // exchange buffers of this plane (floats): alternate between 0 and the buffer size
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        xch[v * TI * 32 + T.xs] = ib_[v].x;
+        xch[(8 + v) * TI * 32 + T.xs] = ib_[v].y;
+    }
+    int s2 = 2;          // stage of plane k+2
+    uint32_t par = 0x3;  // bit s = parity of the next wait on stage s: stages 0,1 were waited once in the prologue
+#pragma unroll 1
+    for (int k = ks; k < kb; ++k) {
+        const int s1 = (s2 + NS - 1) % NS, s0 = (s2 + NS - 2) % NS;
+        const float* xq = xch + xsel;   // Qint(k) rows, stored during the previous iteration
+        const float* fxc = fxb + fsel;
+        const float* gyc = gyb + gsel;
+        xsel ^= G::XBUF; fsel ^= G::FXBUF; gsel ^= G::GYBUF;
+        mbar_wait(&full[s2], (par >> s2) & 1u);
+        par ^= 1u << s2;
+        __syncthreads();
+        // stage s0 held plane k: every warp finished reading it (iteration k-1) before the barrier above; refill it two
+        // planes ahead of its use
+        if (producer && k + NS <= klast) issue(k + NS, s0);
+        carry_predict<PATH, TI>(A, T, role, gcol, k + 1 == A.hi_plane, tiles + s1 * G::STAGE_FLOATS, tiles + s2 * G::STAGE_FLOATS, fxc, gyc,
+                                fxb + fsel, gyb + gsel, qa, qb, qc, Xb, Xc, ic);
+        {   // publish the rows of Qint(k+1) for the next plane now, among the arithmetic, instead of in front of the barrier:
+            // that buffer was last read in iteration k-1, which every warp finished before this iteration's barrier
+            float* xn = xch + xsel;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                xn[v * TI * 32 + T.xs] = ic[v].x;
+                xn[(8 + v) * TI * 32 + T.xs] = ic[v].y;
+            }
+        }
+        pair_correct<PATH, TI>(A, T, k >= ka, xq, qa, ia, ib_, ic, outp);
+        outp += P.plane;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            qa[v] = qb[v]; qb[v] = qc[v];
+            ia[v] = ib_[v]; ib_[v] = ic[v];
+        }
+        Xb = Xc;
+        s2 = (s2 + 1) % NS;
+    }
+}
+
 // -----------------------------------------------------------------------------------------------
 // Remainder strip.  The tiles of the hot kernel produce 30 (path A: 31) output columns each; when Ny leaves a
 // remainder of a few columns (304 -> 10 x 30 + 2) a whole extra tile column -- 9 % of the launch at 304 -- would
@@ -856,8 +1311,8 @@ constexpr int kStripRows = 6;   // at most this many compute rows
 #ifndef IMHD_STRIP_REGS
 #define IMHD_STRIP_REGS 168
 #endif
-template <int PATH>
-__global__ void __maxnreg__(IMHD_STRIP_REGS) k_fused_strip(const FusedArgs A, const __grid_constant__ CUtensorMap tmap) {
+template <int PATH, int REGS = IMHD_STRIP_REGS>
+__global__ void __maxnreg__(REGS) k_fused_strip(const FusedArgs A, const __grid_constant__ CUtensorMap tmap) {
     constexpr int O = Ring<PATH>::O;
     constexpr int WL = 32 - 2 * O;
     // The staging tile of a plane is ONE TMA box (12 columns x 32 rows x 8 variables, dense: row pitch 12 floats), four
@@ -1167,10 +1622,18 @@ static PFN_cuTensorMapEncodeTiled get_encode() {
     return fn;
 }
 
-static int g_force_ldg = 0, g_no_strip = 0, g_force_strip = 0, g_kernel = 0;
+static int g_force_ldg = 0, g_no_strip = 0, g_force_strip = 0, g_kernel = 0, g_co_strip = 0;
 extern "C" void imhd_set_kernel_variant(int flags) {
-    g_force_ldg = flags & 1; g_no_strip = (flags >> 1) & 1; g_force_strip = (flags >> 2) & 1; g_kernel = (flags >> 4) & 15;
+    g_force_ldg = flags & 1; g_no_strip = (flags >> 1) & 1; g_force_strip = (flags >> 2) & 1; g_co_strip = (flags >> 3) & 1;
+    g_kernel = (flags >> 4) & 15;
 }
+
+// Side stream of the co-resident remainder strip (one per device; the fork / launch / join triple is enqueued under the mutex).
+namespace {
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+SideStream g_side[64];
+std::mutex g_side_mu;
+}  // namespace
 
 // 4-D view (j, i, plane, variable) of a state array for the tile loads of the TMA kernel.
 static bool make_tile_map(CUtensorMap* map, const FusedArgs& A, int nplanes, int tile_rows, int tile_cols = kTC,
@@ -1241,6 +1704,21 @@ struct PairLaunch {
     static constexpr int THREAD_ROWS = TI;
     static constexpr int BLOCKS_PER_SM = MINB;
     static auto kernel() { return k_fused_pair<PATH, TI, MINB>; }
+};
+
+template <int PATH, int TI, int MINB = 1>
+struct SplitLaunch {
+    using G = SplitGeo<PATH, TI>;
+    static constexpr int THREAD_ROWS = TI;
+    static constexpr int BLOCKS_PER_SM = MINB;
+    static auto kernel() { return k_fused_split<PATH, TI, MINB>; }
+};
+template <int PATH, int TI, int MINB = 1>
+struct CarryLaunch {
+    using G = CarryGeo<PATH, TI>;
+    static constexpr int THREAD_ROWS = TI;
+    static constexpr int BLOCKS_PER_SM = MINB;
+    static auto kernel() { return k_fused_carry<PATH, TI, MINB>; }
 };
 
 // ---- optional per-launch timing of the hot kernel (bench.py's roofline leg) ---------------------------------------------
@@ -1320,6 +1798,26 @@ static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, int nplanes_array, 
     static unsigned long long done = 0;
     if (int e = ensure_smem(L::kernel(), G::SMEM, done)) return e;
     TimedLaunch* timed = timing_begin(A, nz, st);
+    // Co-resident strip: a hot block leaves 10240 registers and ~100 KB of shared memory of its SM idle, and the strip is a
+    // latency chain (IPC 0.7) -- so the strip runs UNDER the hot kernel instead of after it: one 128-thread block per SM at
+    // an 80-register cap, on a high-priority side stream forked in front of the hot launch and joined behind it.
+    const bool co = strip && g_co_strip && L::BLOCKS_PER_SM == 1;
+    SideStream* side = nullptr;
+    std::unique_lock<std::mutex> side_lock;
+    if (co) {
+        int dev = 0;
+        IMHD_CUDA(cudaGetDevice(&dev));
+        side_lock = std::unique_lock<std::mutex>(g_side_mu);
+        side = &g_side[dev & 63];
+        if (!side->s) {
+            int lo = 0, hi = 0;
+            IMHD_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            IMHD_CUDA(cudaStreamCreateWithPriority(&side->s, cudaStreamNonBlocking, hi));
+            IMHD_CUDA(cudaEventCreateWithFlags(&side->fork, cudaEventDisableTiming));
+            IMHD_CUDA(cudaEventCreateWithFlags(&side->join, cudaEventDisableTiming));
+        }
+        IMHD_CUDA(cudaEventRecord(side->fork, st));
+    }
     L::kernel()<<<dim3(grid_j, A.ntile_i, nchunk), dim3(32, L::THREAD_ROWS), G::SMEM, st>>>(A, tmap);
     IMHD_LAUNCH_CHECK(1);
     if (strip) {
@@ -1331,6 +1829,7 @@ static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, int nplanes_array, 
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         int n = (3 * sms + S.ntile_i - 1) / S.ntile_i;      // a few small blocks per SM
+        if (co) n = sms / S.ntile_i;                        // co-resident: one block per SM, all resident from the start
         n = n > nz / 8 ? nz / 8 : n;
         n = n < 1 ? 1 : n;
         S.chunk = (nz + n - 1) / n;
@@ -1344,8 +1843,18 @@ static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, int nplanes_array, 
         // 128-byte promotion (and, measured, "none") fetch 277 MB -- for 46 MB needed.  The kernel's duration does not
         // depend on it (nor on cp.async vs TMA staging, nor on its register cap): see tools/experiments/README.md.
         if (!make_tile_map(&smap, A, nplanes_array, 32, kStripCols, CU_TENSOR_MAP_L2_PROMOTION_L2_64B)) { set_error("remainder strip: tensor map"); return IMHD_E_STATE; }
-        k_fused_strip<PATH><<<dim3(S.ntile_i, 1, (nz + S.chunk - 1) / S.chunk), dim3(32, strip_rows), strip_smem, st>>>(S, smap);
-        IMHD_LAUNCH_CHECK(1);
+        if (co) {
+            static unsigned long long cdone = 0;
+            if (int e = ensure_smem(k_fused_strip<PATH, 80>, strip_smem, cdone)) return e;
+            IMHD_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+            k_fused_strip<PATH, 80><<<dim3(S.ntile_i, 1, (nz + S.chunk - 1) / S.chunk), dim3(32, strip_rows), strip_smem, side->s>>>(S, smap);
+            IMHD_LAUNCH_CHECK(1);
+            IMHD_CUDA(cudaEventRecord(side->join, side->s));
+            IMHD_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+        } else {
+            k_fused_strip<PATH><<<dim3(S.ntile_i, 1, (nz + S.chunk - 1) / S.chunk), dim3(32, strip_rows), strip_smem, st>>>(S, smap);
+            IMHD_LAUNCH_CHECK(1);
+        }
     }
     timing_end(timed, st);
     return 0;
@@ -1365,6 +1874,12 @@ static int launch_fused(FusedArgs& A, int nplanes_array, cudaStream_t st) {
         case 2:  // the 8-warp tile for either path
             if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, PairLaunch<PATH, 8>>(A, tmap, nplanes_array, st);
             break;
+        case 4:  // split-phase exchange barrier on the 8-warp tile
+            if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, SplitLaunch<PATH, 8>>(A, tmap, nplanes_array, st);
+            break;
+        case 3:  // carried fluxes on the 8-warp tile
+            if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, CarryLaunch<PATH, 8>>(A, tmap, nplanes_array, st);
+            break;
         default:
             // Path B: 8 warps x 2 rows = a 16x32 tile, one block per SM (its two-row ring makes smaller tiles too wasteful:
             // 4-warp tiles, 2 or 3 blocks per SM, measure 30.3 / 28.2 GLUPS against 32.0).  Path A: one ring row and ~170
@@ -1372,7 +1887,7 @@ static int launch_fused(FusedArgs& A, int nplanes_array, cudaStream_t st) {
             if (PATH == IMHD_PATH_A) {
                 if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 4>::TR)) return launch_tma<PATH, PairLaunch<PATH, 4, 3>>(A, tmap, nplanes_array, st);
             } else {
-                if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, PairLaunch<PATH, 8>>(A, tmap, nplanes_array, st);
+                if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, SplitLaunch<PATH, 8>>(A, tmap, nplanes_array, st);
             }
             break;
     }
