@@ -1035,7 +1035,8 @@ struct CarryGeo : PairGeo<PATH, TI> {
     static constexpr int GYP = 33;                   // row pitch of the published y fluxes: 32 lanes + the column right of the tile
     static constexpr int GYV = B::NR * GYP;
     static constexpr int GYBUF = 6 * GYV;
-    static constexpr size_t SMEM = B::NSTAGE * B::STAGE_BYTES + (B::NXBUF * B::XBUF + 2 * FXBUF + 2 * GYBUF) * 4 + 64;
+    static constexpr int NXBUF = 4;                  // split-phase Qint exchange (see SplitGeo)
+    static constexpr size_t SMEM = B::NSTAGE * B::STAGE_BYTES + (NXBUF * B::XBUF + 2 * FXBUF + 2 * GYBUF) * 4 + 128;
 };
 
 // Fluxes of plane k+2 (tile tq2) -> registers (Xn) and the NEXT plane's exchange buffers (fxn, gyn); predictor of plane
@@ -1043,14 +1044,17 @@ struct CarryGeo : PairGeo<PATH, TI> {
 template <int PATH, int TI>
 __device__ __forceinline__ void carry_predict(const FusedArgs& A, const PairThread& T, int role, int gcol, bool hi, const float* tq1,
                                               const float* tq2, const float* fxc, const float* gyc, float* fxn, float* gyn,
-                                              const float2 (&q0)[8], const float2 (&q1)[8], float2 (&qn)[8],
+                                              uint64_t* ybar, const float2 (&q0)[8], const float2 (&q1)[8], float2 (&qn)[8],
                                               const FluxQ<float2>& X1, FluxQ<float2>& Xn, float2 (&qip)[8]) {
     using G = CarryGeo<PATH, TI>;
     const Params& P = A.P;
     constexpr int VS = G::TR * kTC;   // variable stride inside a tile
     const FlagT<float2> right = {T.right(), T.right()};
     const int lane = T.xs & 31, ti = T.xs >> 5;
-    // this plane's neighbour values first: their latency hides under the flux evaluation below
+    // plane k+2 first (the flux evaluation wants it first), then this plane's neighbour values: their latency hides under
+    // the flux evaluation
+#pragma unroll
+    for (int v = 0; v < 8; ++v) qn[v] = make_float2(tq2[v * VS + T.own], tq2[v * VS + T.own + kTC]);
     float xlast[8], xfirst[8], fl[8];
     float2 yp[8], ym[8], gy[8];
 #pragma unroll
@@ -1076,9 +1080,7 @@ __device__ __forceinline__ void carry_predict(const FusedArgs& A, const PairThre
         gy[BZ] = make_float2(gp[4 * G::GYV], gp[4 * G::GYV + G::GYP]);
         gy[EN] = make_float2(gp[5 * G::GYV], gp[5 * G::GYV + G::GYP]);
     }
-    // ---- plane k+2: own state, its fluxes, and what the neighbours will want of them next iteration ----------------
-#pragma unroll
-    for (int v = 0; v < 8; ++v) qn[v] = make_float2(tq2[v * VS + T.own], tq2[v * VS + T.own + kTC]);
+    // ---- plane k+2: its fluxes, and what the neighbours will want of them next iteration ---------------------------
     flux_all(qn, Xn);
     {
         float* fp = fxn + ti * 32 + lane;
@@ -1107,6 +1109,7 @@ __device__ __forceinline__ void carry_predict(const FusedArgs& A, const PairThre
             gp[3 * G::GYV] = t[BX]; gp[4 * G::GYV] = t[BZ]; gp[5 * G::GYV] = t[EN];
         }
     }
+    mbar_arrive(ybar);
     // ---- predictor of plane k+1 -----------------------------------------------------------------------------
     {
         float2 f[8], g[8], h1[8], hn[8], dF[8], xsum[8];
@@ -1144,6 +1147,8 @@ __global__ void __launch_bounds__(TI * 32, MINB) k_fused_carry(const FusedArgs A
     float* fxb = xch + G::NXBUF * G::XBUF;                                    // [2][6][TI+1][32]  F(Q), first rows + the row below the tile
     float* gyb = fxb + 2 * G::FXBUF;                                          // [2][6][NR][33]    G(Q), all rows + the column right of the tile
     uint64_t* full = reinterpret_cast<uint64_t*>(gyb + 2 * G::GYBUF);         // [NS] tile landed
+    uint64_t* xbar = full + NS;                                               // [2] Qint rows of a plane published (even / odd planes)
+    uint64_t* ybar = xbar + 2;                                                // [1] fluxes of a plane published
 
     const Params& P = A.P;
     const int lane = threadIdx.x, ti = threadIdx.y;
@@ -1192,6 +1197,9 @@ __global__ void __launch_bounds__(TI * 32, MINB) k_fused_carry(const FusedArgs A
 
     if (producer) {
         for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+        mbar_init(&xbar[0], TI * 32);
+        mbar_init(&xbar[1], TI * 32);
+        mbar_init(&ybar[0], TI * 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async;" ::: "memory");
     }
@@ -1248,40 +1256,48 @@ __global__ void __launch_bounds__(TI * 32, MINB) k_fused_carry(const FusedArgs A
         }
     }
 
+    mbar_arrive(&ybar[0]);
     // output pointer of the first row at plane ks; stores are predicated off below plane ka
     float* outp = A.Qout + (long long)(ks - A.kbase) * P.plane + (long long)i0 * P.Ny + T.jc;
-    int xsel = 0, fsel = 0, gsel = 0;   // exchange buffers of this plane (floats): alternate between 0 and the buffer size
+    int xr = 0, fsel = 0, gsel = 0;   // exchange buffers of this plane: Qint rows (index, four buffers), fluxes (floats, two)
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
         xch[v * TI * 32 + T.xs] = ib_[v].x;
         xch[(8 + v) * TI * 32 + T.xs] = ib_[v].y;
     }
+    mbar_arrive(&xbar[0]);
+    uint32_t xpar = 0, ypar = 0;
     int s2 = 2;          // stage of plane k+2
     uint32_t par = 0x3;  // bit s = parity of the next wait on stage s: stages 0,1 were waited once in the prologue
 #pragma unroll 1
     for (int k = ks; k < kb; ++k) {
         const int s1 = (s2 + NS - 1) % NS, s0 = (s2 + NS - 2) % NS;
-        const float* xq = xch + xsel;   // Qint(k) rows, stored during the previous iteration
+        const float* xq = xch + xr * G::XBUF;   // Qint(k) rows, stored during the previous iteration
+        const int xb = xr & 1;
+        xr = (xr + 1) & 3;
         const float* fxc = fxb + fsel;
         const float* gyc = gyb + gsel;
-        xsel ^= G::XBUF; fsel ^= G::FXBUF; gsel ^= G::GYBUF;
+        fsel ^= G::FXBUF; gsel ^= G::GYBUF;
         mbar_wait(&full[s2], (par >> s2) & 1u);
         par ^= 1u << s2;
-        __syncthreads();
-        // stage s0 held plane k: every warp finished reading it (iteration k-1) before the barrier above; refill it two
-        // planes ahead of its use
-        if (producer && k + NS <= klast) issue(k + NS, s0);
+        // the neighbours' fluxes of plane k+1: published early in their iteration k-1.  Passing this wait also means every
+        // warp has read the fluxes of plane k (it does so before it publishes), whose buffers this iteration overwrites.
+        mbar_wait(&ybar[0], ypar);
+        ypar ^= 1u;
         carry_predict<PATH, TI>(A, T, role, gcol, k + 1 == A.hi_plane, tiles + s1 * G::STAGE_FLOATS, tiles + s2 * G::STAGE_FLOATS, fxc, gyc,
-                                fxb + fsel, gyb + gsel, qa, qb, qc, Xb, Xc, ic);
-        {   // publish the rows of Qint(k+1) for the next plane now, among the arithmetic, instead of in front of the barrier:
-            // that buffer was last read in iteration k-1, which every warp finished before this iteration's barrier
-            float* xn = xch + xsel;
+                                fxb + fsel, gyb + gsel, ybar, qa, qb, qc, Xb, Xc, ic);
+        {
+            float* xn = xch + xr * G::XBUF;
 #pragma unroll
             for (int v = 0; v < 8; ++v) {
                 xn[v * TI * 32 + T.xs] = ic[v].x;
                 xn[(8 + v) * TI * 32 + T.xs] = ic[v].y;
             }
+            mbar_arrive(&xbar[xb ^ 1]);
         }
+        mbar_wait(&xbar[xb], (xpar >> xb) & 1u);
+        xpar ^= 1u << xb;
+        if (producer && k + NS <= klast) issue(k + NS, s0);
         pair_correct<PATH, TI>(A, T, k >= ka, xq, qa, ia, ib_, ic, outp);
         outp += P.plane;
 #pragma unroll
@@ -1440,6 +1456,220 @@ __global__ void __maxnreg__(REGS) k_fused_strip(const FusedArgs A, const __grid_
             qim[v] = qic[v]; qic[v] = qip[v];
         }
     }
+}
+
+// -----------------------------------------------------------------------------------------------
+// Remainder strip, warp-autonomous (the one the launcher prefers when the strip is at most four columns wide).
+// One WARP owns a 16-row x 4-column tile of the strip -- lane = 4 * r + c: thread row r = 0..7 (two rows each, packed as
+// in k_fused_pair), column c = 0..3 (c = 0 is the predictor-only ring column = the last output column of the marching
+// kernel) -- and marches along k on its own: no shared memory, no block barrier, no TMA.  Everything a cell needs from
+// its neighbours inside the tile travels by warp shuffle (rows: +-4 lanes, columns: +-1 lane): the neighbour STATES of
+// Q(k+1) and Qint(k), and the neighbour FLUXES G(j+-1), F(i+1), F'(i-1), which the neighbouring lane evaluates as its
+// own anyway; the one row above / below the tile and the one column left of it are loaded by the lanes at that edge.
+// Four lanes read 16 contiguous bytes of a row, so a load instruction touches 8 sectors instead of the 32 of the
+// lanes-along-i strip; the loads go straight to registers and their latency is hidden by the other warps of the SM
+// (eight independent warps).  Same device functions on the same values -> the same bits (tests).
+// -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float shdn(float x, int d) { return __shfl_down_sync(0xffffffffu, x, d); }
+__device__ __forceinline__ float shup(float x, int d) { return __shfl_up_sync(0xffffffffu, x, d); }
+__device__ __forceinline__ float2 shdn2(float2 x, int d) { return make_float2(shdn(x.x, d), shdn(x.y, d)); }
+__device__ __forceinline__ float2 shup2(float2 x, int d) { return make_float2(shup(x.x, d), shup(x.y, d)); }
+
+constexpr int kWsCols = 5;                    // staged columns: the one left of the tile + the tile's four
+constexpr int kWsRows = 18;                   // staged rows: the tile's sixteen + one above + one below
+constexpr int kWsVar = kWsRows * kWsCols;     // variable stride inside a stage
+constexpr int kWsStage = 8 * kWsVar;          // floats per staged plane
+constexpr int kWsNst = 4;                     // planes k+1, k+2 in use, k+3, k+4 in flight
+constexpr size_t kWsSmem = 4 * kWsNst * kWsStage * sizeof(float);   // four warps per block
+
+template <int PATH>
+__global__ void __launch_bounds__(128, 2) k_fused_wstrip(const FusedArgs A) {
+    constexpr int NR = 16;
+    constexpr int WI = PATH == IMHD_PATH_A ? NR - 1 : NR - 2;
+    extern __shared__ __align__(16) float ws_smem[];
+    const Params& P = A.P;
+    const int lane = threadIdx.x & 31;
+    float* ring = ws_smem + (threadIdx.x >> 5) * (kWsNst * kWsStage);   // this warp's private staging ring
+    const int w = blockIdx.x * 4 + (threadIdx.x >> 5);      // warp tile: tile row bi, z chunk cz
+    const int bi = w % A.ntile_i, cz = w / A.ntile_i;
+    const int ka = A.kfrom + cz * A.chunk, kb = min(ka + A.chunk, A.kto);
+    if (ka >= A.kto) return;                                 // warp-uniform
+    const int r = lane >> 2, c = lane & 3;
+    const int ib = bi * WI, t0 = 2 * r, i0 = ib + t0, j = A.jstrip + 1 + c;
+    const int oi_lo = bi == 0 ? 0 : ib + 1, oi_hi = bi == A.ntile_i - 1 ? P.Nx : ib + WI + 1;
+    PairThread T;
+    T.rows = 0;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int i = i0 + rr, t = t0 + rr;
+        const bool corr_row = t >= 1 && (PATH == IMHD_PATH_A || t <= NR - 2);
+        if (i == P.Nx - 1) T.rows |= 1u << rr;
+        if (i > 0 && i < P.Nx - 1) T.rows |= 1u << (8 + rr);
+        if (corr_row && i > 0 && (PATH == IMHD_PATH_A ? i < P.Nx : i < P.Nx - 1)) T.rows |= 1u << (16 + rr);
+        if (i < P.Nx && i >= oi_lo && i < oi_hi) T.rows |= 1u << (24 + rr);
+    }
+    const bool interior_j = j > 0 && j < P.Ny - 1;
+    T.lanes = (j == P.Ny - 1 ? 1u : 0u) | (interior_j ? 2u : 0u) |
+              ((PATH == IMHD_PATH_A ? (j > 0 && j < P.Ny) : interior_j) ? 4u : 0u) | ((j < P.Ny && c >= 1) ? 8u : 0u);
+    T.i0 = i0;
+    T.jc = min(j, P.Ny - 1);
+    T.own = (t0 + 1) * kWsCols + c + 1;                      // first row of the thread inside a staged plane
+    keep(T.rows); keep(T.lanes); keep(T.own);
+    const int ic0 = min(i0, P.Nx - 1), ic1 = min(i0 + 1, P.Nx - 1);
+    const FlagT<float2> right = {T.right(), T.right()};
+
+    const bool first = ka == A.ka0;
+    const int ks = first ? ka - 1 : ka - 2;
+    const int klast = kb + 1;  // last plane any iteration reads
+
+    // Loader: lanes 0..29 copy 6 rows x 5 columns of one variable per pass (three passes cover the 18 staged rows), four
+    // bytes per cp.async; rows / columns outside the domain repeat the edge (they only feed discarded results).
+    int goff[3];
+    {
+        const int lr = lane / kWsCols, lc = lane % kWsCols;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+            goff[p] = min(max(ib - 1 + p * 6 + lr, 0), P.Nx - 1) * P.Ny + min(A.jstrip + lc, P.Ny - 1);
+    }
+    const uint32_t ring_u32 = smem_u32(ring) + 4u * lane;
+    auto fill = [&](int k) {   // plane k -> stage (k - ks) & 3; always one commit group
+        if (k <= klast && lane < 30) {
+            const float* src = A.Qin + (long long)(min(max(k, A.kmin), A.kmax) - A.kbase) * P.plane;
+            const uint32_t dst = ring_u32 + 4u * (((k - ks) & (kWsNst - 1)) * kWsStage);
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (v * kWsVar + p * 30)),
+                                 "l"(src + v * A.vs + goff[p])
+                                 : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto stage = [&](int k) -> const float* { return ring + ((k - ks) & (kWsNst - 1)) * kWsStage; };
+
+    for (int q = 0; q < kWsNst; ++q) fill(ks + q);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    __syncwarp();
+
+    float2 qa[8], qb[8], qc[8], hb[8], hc[8], ia[8], ib_[8], ic[8];
+    PrimT<float2> pb, pc;
+    {
+        const float* sa = stage(ks);
+        const float* sb = stage(ks + 1);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            qa[v] = make_float2(sa[v * kWsVar + T.own], sa[v * kWsVar + T.own + kWsCols]);
+            qb[v] = make_float2(sb[v * kWsVar + T.own], sb[v * kWsVar + T.own + kWsCols]);
+            ia[v] = make_float2(1.0f, 1.0f);
+            ib_[v] = make_float2(1.0f, 1.0f);
+        }
+    }
+    pb = make_prim(qb);
+    flux_idx<DIR_Z>(qb, pb, hb);
+    if (first) {
+        float a[8], b[8];
+        ldg8(A.qlo, (long long)ic0 * P.Ny + T.jc, P.plane, a);
+        ldg8(A.qlo, (long long)ic1 * P.Ny + T.jc, P.plane, b);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) ib_[v] = make_float2(a[v], b[v]);
+    }
+    float* outp = A.Qout + (long long)(ks - A.kbase) * P.plane + (long long)i0 * P.Ny + T.jc;
+
+#pragma unroll 1
+    for (int k = ks; k < kb; ++k) {
+        // plane k+2 has landed (the two fills behind it may still be in flight); every lane is past its reads of plane k
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        fill(k + kWsNst);
+        const float* tq1 = stage(k + 1);
+        const float* tq2 = stage(k + 2);
+        // ---- predictor of plane k+1 -------------------------------------------------------------------------
+#pragma unroll
+        for (int v = 0; v < 8; ++v) qc[v] = make_float2(tq2[v * kWsVar + T.own], tq2[v * kWsVar + T.own + kWsCols]);
+        pc = make_prim(qc);
+        flux_idx<DIR_Z>(qc, pc, hc);
+        {
+            float xlast[8], xfirst[8], fl[8];
+            float2 yp[8], ym[8], f[8], g[8], gy[8], dF[8], xsum[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                xlast[v] = tq1[v * kWsVar + T.own + 2 * kWsCols];       // Q(k+1) one row below the thread's rows
+                yp[v] = make_float2(tq1[v * kWsVar + T.own + 1], tq1[v * kWsVar + T.own + kWsCols + 1]);
+                if (PATH == IMHD_PATH_B) {
+                    xfirst[v] = tq1[v * kWsVar + T.own - kWsCols];      // ... and one row above
+                    ym[v] = make_float2(tq1[v * kWsVar + T.own - 1], tq1[v * kWsVar + T.own + kWsCols - 1]);
+                }
+            }
+            flux_idx<DIR_X>(qb, pb, f);
+            flux_idx<DIR_X>(xlast, make_prim(xlast), fl);
+            flux_idx<DIR_Y>(qb, pb, g);
+            // G(Q(k+1)) one column right: the lane to the right has just evaluated it as its own (the tile's last column never
+            // needs it: it is the wall or outside the domain)
+#pragma unroll
+            for (int v = 0; v < 8; ++v) gy[v] = v == RHO ? yp[MY] : (v == BY ? make_float2(0.0f, 0.0f) : shdn2(g[v], 1));
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                dF[v].x = T.bottom(0) ? -f[v].x : f[v].y - f[v].x;
+                dF[v].y = T.bottom(1) ? -f[v].y : fl[v] - f[v].y;
+                if (PATH == IMHD_PATH_B) xsum[v] = make_float2(qb[v].y + xfirst[v], xlast[v] + qb[v].x);
+            }
+            qint_combine<PATH, float2>(qb, dF, g, gy, hb, hc, xsum, ym, yp, qa, qc, {T.bottom(0), T.bottom(1)}, right,
+                                       {T.interior_i(0) && T.interior_j(), T.interior_i(1) && T.interior_j()}, P, ic);
+        }
+        if (__builtin_expect(k + 1 == A.hi_plane, 0)) {
+            float a[8], b[8];
+            ldg8(A.qhi, (long long)ic0 * P.Ny + T.jc, P.plane, a);
+            ldg8(A.qhi, (long long)ic1 * P.Ny + T.jc, P.plane, b);
+#pragma unroll
+            for (int v = 0; v < 8; ++v) ic[v] = make_float2(a[v], b[v]);
+        }
+        // ---- corrector of plane k ---------------------------------------------------------------------------
+        {
+            float xfirst[8], xlast[8];
+            float2 fc[8], gc[8], hcc[8], gj[8], hk[8], ym[8], yp[8], dF[8], xsum[8], out[8];
+            const PrimT<float2> sc = make_prim(ib_);
+            flux_loc<DIR_X>(ib_, sc, fc);
+            flux_loc<DIR_Y>(ib_, sc, gc);
+            flux_loc<DIR_Z>(ib_, sc, hcc);
+#pragma unroll
+            for (int v = 0; v < 8; ++v) xfirst[v] = shup(ib_[v].y, 4);   // Qint(k), second row of the thread row above
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                if (PATH == IMHD_PATH_B) xlast[v] = shdn(ib_[v].x, 4);
+                ym[v] = shup2(ib_[v], 1);
+                if (PATH == IMHD_PATH_B) yp[v] = shdn2(ib_[v], 1);
+                gj[v] = v == BY ? make_float2(0.0f, 0.0f) : shup2(gc[v], 1);
+                // F'(Qint(i-1)): the thread row above evaluated it as the flux of its second row (B-6: rho)
+                const float ff = (v == RHO) ? xfirst[MX] : (v == BX ? 0.0f : shup(fc[v].y, 4));
+                const float fa = (PATH == IMHD_PATH_B && v == RHO) ? xfirst[RHO] : ff;
+                const float fb = (PATH == IMHD_PATH_B && v == RHO) ? ib_[RHO].x : fc[v].x;
+                dF[v] = make_float2(fc[v].x - fa, fc[v].y - fb);
+                if (PATH == IMHD_PATH_B) xsum[v] = make_float2(ib_[v].y + xfirst[v], xlast[v] + ib_[v].x);
+            }
+            hflux_km1<float2>(ia, make_float2(xfirst[BX], ib_[BX].x), ym[BY], ym[MY], hk);
+            corr_combine<PATH, float2>(qa, ib_, dF, gc, gj, hcc, hk, xsum, ym, yp, ia, ic, P, out);
+            if (k >= ka && T.owner_j()) {
+                const bool ua = T.upd_i(0) && T.upd_j(), ub = T.upd_i(1) && T.upd_j();
+                if (T.owner_i(0)) {
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) outp[v * A.vs] = ua ? out[v].x : qa[v].x;
+                }
+                if (T.owner_i(1)) {
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) outp[v * A.vs + P.Ny] = ub ? out[v].y : qa[v].y;
+                }
+            }
+        }
+        outp += P.plane;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            qa[v] = qb[v]; qb[v] = qc[v]; hb[v] = hc[v];
+            ia[v] = ib_[v]; ib_[v] = ic[v];
+        }
+        pb = pc;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // Predictor plane k (global index, k <= Nz-2) into an (8,Nx,Ny) buffer: same device function, same
@@ -1622,10 +1852,10 @@ static PFN_cuTensorMapEncodeTiled get_encode() {
     return fn;
 }
 
-static int g_force_ldg = 0, g_no_strip = 0, g_force_strip = 0, g_kernel = 0, g_co_strip = 0;
+static int g_force_ldg = 0, g_no_strip = 0, g_force_strip = 0, g_kernel = 0, g_co_strip = 0, g_block_strip = 0;
 extern "C" void imhd_set_kernel_variant(int flags) {
     g_force_ldg = flags & 1; g_no_strip = (flags >> 1) & 1; g_force_strip = (flags >> 2) & 1; g_co_strip = (flags >> 3) & 1;
-    g_kernel = (flags >> 4) & 15;
+    g_kernel = (flags >> 4) & 15; g_block_strip = (flags >> 8) & 1;
 }
 
 // Side stream of the co-resident remainder strip (one per device; the fork / launch / join triple is enqueued under the mutex).
@@ -1820,7 +2050,27 @@ static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, int nplanes_array, 
     }
     L::kernel()<<<dim3(grid_j, A.ntile_i, nchunk), dim3(32, L::THREAD_ROWS), G::SMEM, st>>>(A, tmap);
     IMHD_LAUNCH_CHECK(1);
-    if (strip) {
+    if (strip && strip_rows <= 4 && !g_block_strip && !co) {
+        // warp-autonomous strip: one warp per 16-row x 4-column tile and z chunk, eight warps per SM
+        FusedArgs S = A;
+        constexpr int WIw = PATH == IMHD_PATH_A ? 15 : 14;
+        S.ntile_i = (ni + WIw - 1) / WIw;
+        S.jstrip = grid_j * G::WJ - 1;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int n = (8 * sms) / S.ntile_i;                        // one wave of warps
+        n = n > nz / 8 ? nz / 8 : n;
+        n = n < 1 ? 1 : n;
+        S.chunk = (nz + n - 1) / n;
+        if (g_chunk_override > 0) S.chunk = g_chunk_override;
+        S.chunk = S.chunk < 2 ? 2 : (S.chunk > nz ? nz : S.chunk);
+        const int warps = S.ntile_i * ((nz + S.chunk - 1) / S.chunk);
+        static unsigned long long wdone = 0;
+        if (int e = ensure_smem(k_fused_wstrip<PATH>, kWsSmem, wdone)) return e;
+        k_fused_wstrip<PATH><<<(warps + 3) / 4, 128, kWsSmem, st>>>(S);
+        IMHD_LAUNCH_CHECK(1);
+    } else if (strip) {
         FusedArgs S = A;
         constexpr int WL = 32 - 2 * O;
         S.ntile_i = (ni + WL - 1) / WL;
