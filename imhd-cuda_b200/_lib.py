@@ -56,6 +56,7 @@ SIGNATURES = {
     "imhd_init_screwpinch": (_i, [_p, _f, _f, _p, _p, _p] + _dims + [_p]),
     "imhd_step_fused": (_i, [_p, _p, _p, _p, _p, C.POINTER(Slab), _p]),
     "imhd_step_fused_planes": (_i, [_p, _p, _p, _p, _p, C.POINTER(Slab), _i, _i, _p]),
+    "imhd_step_fused_ends": (_i, [_p, _p, _p, _p, _p, C.POINTER(Slab), _i, _i, _i, _i, _p]),
     "imhd_stability_scan": (_i, [_p, C.POINTER(Slab), C.POINTER(Stability), _p]),
     "imhd_ctx_stability": (_i, [_p, _f, C.POINTER(Stability)]),
     "imhd_wall_energy_fixed_point": (_f, [_f, _i]),

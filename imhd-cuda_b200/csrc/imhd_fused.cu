@@ -49,11 +49,16 @@ struct FusedArgs {
     int k0, k1;         // owned (written) global planes [k0, k1)
     int ka0, kb0;       // planes the marching kernel owns: [max(k0,1), min(k1, A: Nz / B: Nz-1))
     int kfrom, kto;     // planes THIS launch writes, a sub-range of [ka0, kb0) (comm/compute overlap launches the slab ends first)
+    int clen, pad_[3];  // planes per z-chunk.  clen == chunk: the chunks tile [kfrom, kto).  clen < chunk: a launch over TWO plane
+                        // ranges of clen planes each, [kfrom, kfrom + clen) and [kfrom + chunk, kto) -- both slab ends of the
+                        // multi-GPU loop in one launch (one full set of blocks instead of two half-empty ones).
+                        // pad_: the fields behind keep their offsets modulo 16 -- ptxas pairs constant-bank loads by alignment,
+                        // and another pairing re-colours the registers of the whole plane loop (measured: 3 % slower)
     const float* qlo;   // (8,Nx,Ny) Qint at global plane ka0-1  (own Qint(0) when k0 == 0)
     const float* qhi;   // (8,Nx,Ny) Qint at global plane hi_plane = min(k1, Nz-1)
     const float* qwrap; // (8,Nx,Ny) Qint(Nz-2) == Qint(-1): path B, slab with k0 == 0 only (k=0 face)
     int hi_plane;
-    int chunk;          // owned planes per z-chunk
+    int chunk;          // z-chunk c of a launch starts at plane kfrom + c * chunk and holds clen planes
     int ntile_i, ntile_j;
     int jstrip;         // remainder-strip kernel only: j of its first thread row
     float corner_e;     // path B: fixed-point wall energy of column (Nx-1,Ny-1) (B-8)
@@ -64,6 +69,14 @@ template <int PATH>
 struct Ring {  // halo ring width of a tile
     static constexpr int O = PATH == IMHD_PATH_A ? 1 : 2;
 };
+
+// planes [ka, kb) of z-chunk zc
+// (kept to exactly this arithmetic: the register allocation of the marching kernels' plane loop follows the shape of the
+// prologue, and a select between two ranges here cost the path B kernel 3 % -- tools/experiments/README.md)
+__device__ __forceinline__ void chunk_range(const FusedArgs& A, int zc, int& ka, int& kb) {
+    ka = A.kfrom + zc * A.chunk;
+    kb = min(ka + A.clen, A.kto);
+}
 
 __device__ __forceinline__ void ldg8(const float* __restrict__ A, long long off, long long vs, float U[8]) {
 #pragma unroll
@@ -257,7 +270,8 @@ __global__ void __launch_bounds__(TI * 32, 1) k_fused_step_ldg(const FusedArgs A
     const int tim = max(ti - 1, 0), tip = min(ti + 1, TI - 1);
     const int so = ti * 32 + lane, som = tim * 32 + lane, sop = tip * 32 + lane;  // smem slots: own, i-1, i+1
 
-    const int ka = A.kfrom + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kto);
+    int ka, kb;
+    chunk_range(A, blockIdx.z, ka, kb);
     const bool first = ka == A.ka0;  // the plane below is the slab's qint_lo; otherwise re-derive it in a warm-up plane
     const int ks = first ? ka - 1 : ka - 2;
 
@@ -493,7 +507,8 @@ __global__ void __launch_bounds__(TI * 32, 1) k_fused_step_tma(const FusedArgs A
     T.sop = min(ti + 1, TI - 1) * 32 + lane;
     T.lcol = (long long)min(i, P.Nx - 1) * P.Ny + min(j, P.Ny - 1);
 
-    const int ka = A.kfrom + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kto);
+    int ka, kb;
+    chunk_range(A, blockIdx.z, ka, kb);
     const bool first = ka == A.ka0;  // the plane below is the slab's qint_lo; otherwise re-derive it in a warm-up plane
     const int ks = first ? ka - 1 : ka - 2;
     const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
@@ -611,7 +626,9 @@ struct PairThread {  // per-thread constants
 // One plane of the march for the two rows of a thread, in two phases: predictor plane k+1, corrector plane k.
 // Straight-line on purpose: with 8 warps per SM every taken branch is an instruction-fetch bubble nobody hides, so the
 // tile's ring rows and the warm-up planes run the corrector too and only their STORES are predicated off (`store_ok`).
-template <int PATH, int TI>
+// W = false: the block holds no wall cell, no cell outside the domain and no cell next to one (an "interior" block): every
+// wall / edge select below is decided at compile time.
+template <int PATH, int TI, bool W = true>
 __device__ __forceinline__ void pair_predict(const FusedArgs& A, const PairThread& T, bool hi, const float* tq1, const float* tq2,
                                              const float2 (&q0)[8], const float2 (&q1)[8], float2 (&qn)[8],
                                              const float2 (&h1)[8], float2 (&hn)[8], const PrimT<float2>& p1,
@@ -619,7 +636,9 @@ __device__ __forceinline__ void pair_predict(const FusedArgs& A, const PairThrea
     using G = PairGeo<PATH, TI>;
     const Params& P = A.P;
     constexpr int VS = G::TR * kTC;   // variable stride inside a tile
-    const FlagT<float2> right = {T.right(), T.right()};
+    const bool rt = W && T.right(), b0 = W && T.bottom(0), b1 = W && T.bottom(1);
+    const bool in0 = !W || (T.interior_i(0) && T.interior_j()), in1 = !W || (T.interior_i(1) && T.interior_j());
+    const FlagT<float2> right = {rt, rt};
 #pragma unroll
     for (int v = 0; v < 8; ++v) qn[v] = make_float2(tq2[v * VS + T.own], tq2[v * VS + T.own + kTC]);
     pn = make_prim(qn);
@@ -642,12 +661,11 @@ __device__ __forceinline__ void pair_predict(const FusedArgs& A, const PairThrea
         flux_idx<DIR_Y>(yp, make_prim(yp), gy);
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
-            dF[v].x = T.bottom(0) ? -f[v].x : f[v].y - f[v].x;   // the second row's flux is the first row's i+1 neighbour
-            dF[v].y = T.bottom(1) ? -f[v].y : fl[v] - f[v].y;
+            dF[v].x = b0 ? -f[v].x : f[v].y - f[v].x;   // the second row's flux is the first row's i+1 neighbour
+            dF[v].y = b1 ? -f[v].y : fl[v] - f[v].y;
             if (PATH == IMHD_PATH_B) xsum[v] = make_float2(q1[v].y + xfirst[v], xlast[v] + q1[v].x);
         }
-        qint_combine<PATH, float2>(q1, dF, g, gy, h1, hn, xsum, ym, yp, q0, qn, {T.bottom(0), T.bottom(1)}, right,
-                                   {T.interior_i(0) && T.interior_j(), T.interior_i(1) && T.interior_j()}, P, qip);
+        qint_combine<PATH, float2>(q1, dF, g, gy, h1, hn, xsum, ym, yp, q0, qn, {b0, b1}, right, {in0, in1}, P, qip);
     }
     if (__builtin_expect(hi, 0)) {  // the plane above the slab comes from the neighbour (or is the periodic image): once per slab
         float a[8], b[8];
@@ -658,7 +676,7 @@ __device__ __forceinline__ void pair_predict(const FusedArgs& A, const PairThrea
     }
 }
 
-template <int PATH, int TI>
+template <int PATH, int TI, bool W = true>
 __device__ __forceinline__ void pair_correct(const FusedArgs& A, const PairThread& T, bool store_ok, const float* xq,
                                              const float2 (&q0)[8], const float2 (&qim)[8], const float2 (&qic)[8],
                                              const float2 (&qip)[8], float* outp) {
@@ -692,7 +710,7 @@ __device__ __forceinline__ void pair_correct(const FusedArgs& A, const PairThrea
     hflux_km1<float2>(qim, make_float2(xfirst[BX], qic[BX].x), ym[BY], ym[MY], hk);
     corr_combine<PATH, float2>(q0, qic, dF, gc, gj, hc, hk, xsum, ym, yp, qim, qip, P, out);
     if (store_ok && T.owner_j()) {
-        const bool ua = T.upd_i(0) && T.upd_j(), ub = T.upd_i(1) && T.upd_j();
+        const bool ua = !W || (T.upd_i(0) && T.upd_j()), ub = !W || (T.upd_i(1) && T.upd_j());   // an interior block's owners are all updated
         if (T.owner_i(0)) {
             char* o = reinterpret_cast<char*>(outp);
 #pragma unroll
@@ -752,7 +770,8 @@ __global__ void __launch_bounds__(TI * 32, MINB) k_fused_pair(const FusedArgs A,
     T.jc = min(j, P.Ny - 1);
     keep(T.rows); keep(T.lanes); keep(T.own); keep(T.xs); keep(T.xsm); keep(T.xsp);
 
-    const int ka = A.kfrom + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kto);
+    int ka, kb;
+    chunk_range(A, blockIdx.z, ka, kb);
     const bool first = ka == A.ka0;  // the plane below is the slab's qint_lo; otherwise re-derive it in a warm-up plane
     const int ks = first ? ka - 1 : ka - 2;
     const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
@@ -852,48 +871,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int PATH, int TI, int MINB = 1>
-__global__ void __launch_bounds__(TI * 32, MINB) k_fused_split(const FusedArgs A, const __grid_constant__ CUtensorMap tmap) {
+// The march of one block of k_fused_split (prologue + plane loop).  W = true handles wall cells and cells beyond the
+// domain; W = false would be the body of an interior block, with every wall / edge select folded away at compile time.
+template <int PATH, int TI, bool W>
+__device__ __forceinline__ void split_march(const FusedArgs& A, const CUtensorMap& tmap, const PairThread& T, float* tiles, float* xch,
+                                            uint64_t* full, uint64_t* xbar, int i0, int ib, int c0) {
     using G = SplitGeo<PATH, TI>;
     constexpr int NS = G::NSTAGE;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* tiles = reinterpret_cast<float*>(smem_raw);                       // [NS][8][TR][kTC]
-    float* xch = tiles + NS * G::STAGE_FLOATS;                                // [2][first,last][8][TI][32]  Qint exchange
-    uint64_t* full = reinterpret_cast<uint64_t*>(xch + G::NXBUF * G::XBUF);   // [NS] tile landed
-    uint64_t* xbar = full + NS;                                               // [2] Qint rows of a plane published (even / odd planes)
-
     const Params& P = A.P;
-    const int lane = threadIdx.x, ti = threadIdx.y;
-    const int bi = blockIdx.y, bj = blockIdx.x;
-    const int ib = bi * G::WI, jb = bj * G::WJ;
-    const int t0 = ti * 2, i0 = ib + t0, j = jb + lane;
-    const int oi_lo = bi == 0 ? 0 : ib + 1, oi_hi = bi == A.ntile_i - 1 ? P.Nx : ib + G::WI + 1;
-    const int oj_lo = bj == 0 ? 0 : jb + 1, oj_hi = bj == A.ntile_j - 1 ? P.Ny : jb + G::WJ + 1;
-    PairThread T;
-    T.rows = 0;
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        const int i = i0 + rr, t = t0 + rr;
-        const bool corr_row = t >= 1 && (PATH == IMHD_PATH_A || t <= G::NR - 2);  // rows with valid Qint neighbours
-        if (i == P.Nx - 1) T.rows |= 1u << rr;
-        if (i > 0 && i < P.Nx - 1) T.rows |= 1u << (8 + rr);
-        if (corr_row && i > 0 && (PATH == IMHD_PATH_A ? i < P.Nx : i < P.Nx - 1)) T.rows |= 1u << (16 + rr);
-        if (i < P.Nx && i >= oi_lo && i < oi_hi) T.rows |= 1u << (24 + rr);
-    }
-    const bool interior_j = j > 0 && j < P.Ny - 1;
-    T.lanes = (j == P.Ny - 1 ? 1u : 0u) | (interior_j ? 2u : 0u) |
-              ((PATH == IMHD_PATH_A ? (j > 0 && j < P.Ny) : interior_j) ? 4u : 0u) | ((j < P.Ny && j >= oj_lo && j < oj_hi) ? 8u : 0u);
-    // the box starts at the 4-column boundary at or below jb-1 (measured: a misaligned inner coordinate traps)
-    const int c0 = ((jb - 1 + 4) / 4) * 4 - 4;
-    T.own = (t0 + 1) * kTC + (jb - 1 - c0) + lane + 1;
-    T.xs = ti * 32 + lane;
-    T.xsm = max(ti - 1, 0) * 32 + lane;
-    T.xsp = min(ti + 1, TI - 1) * 32 + lane;
-    T.i0 = i0;
-    T.jc = min(j, P.Ny - 1);
-    keep(T.rows); keep(T.lanes); keep(T.own); keep(T.xs); keep(T.xsm); keep(T.xsp);
-
-    const int ka = A.kfrom + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kto);
+    const int ti = threadIdx.y;
+    (void)ti;
+    int ka, kb;
+    chunk_range(A, blockIdx.z, ka, kb);
     const bool first = ka == A.ka0;  // the plane below is the slab's qint_lo; otherwise re-derive it in a warm-up plane
     const int ks = first ? ka - 1 : ka - 2;
     const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
@@ -958,7 +947,7 @@ __global__ void __launch_bounds__(TI * 32, MINB) k_fused_split(const FusedArgs A
         xr = (xr + 1) & 3;
         mbar_wait(&full[s2], (par >> s2) & 1u);
         par ^= 1u << s2;
-        pair_predict<PATH, TI>(A, T, k + 1 == A.hi_plane, tiles + s1 * G::STAGE_FLOATS, tiles + s2 * G::STAGE_FLOATS, qa, qb, qc, hb, hc,
+        pair_predict<PATH, TI, W>(A, T, k + 1 == A.hi_plane, tiles + s1 * G::STAGE_FLOATS, tiles + s2 * G::STAGE_FLOATS, qa, qb, qc, hb, hc,
                                pb, pc, ic);
         {   // publish the rows of Qint(k+1) for the next plane and say so (release): that buffer last held Qint(k-3), read in
             // iteration k-3, and every warp has been seen in iteration k-2 (its arrival for Qint(k-1), which this warp waited on
@@ -977,7 +966,7 @@ __global__ void __launch_bounds__(TI * 32, MINB) k_fused_split(const FusedArgs A
         xpar ^= 1u << xb;
         // every warp has finished the predictor of iteration k-1, the last reader of the tile of plane k: refill its stage
         if (producer && k + NS <= klast) issue(k + NS, s0);
-        pair_correct<PATH, TI>(A, T, k >= ka, xq, qa, ia, ib_, ic, outp);
+        pair_correct<PATH, TI, W>(A, T, k >= ka, xq, qa, ia, ib_, ic, outp);
         outp += P.plane;
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
@@ -989,166 +978,15 @@ __global__ void __launch_bounds__(TI * 32, MINB) k_fused_split(const FusedArgs A
     }
 }
 
-// -----------------------------------------------------------------------------------------------
-// The register-tiled kernel with CARRIED FLUXES (path B hot path).  Same march, tiles, Qint exchange and corrector as
-// k_fused_pair; what changes is where the predictor's fluxes come from.  k_fused_pair evaluates, per thread and plane,
-// F, G of its own two rows AND G of the column to the right (packed) AND F of the row below (scalar) -- the last two
-// are values the neighbouring lane / thread row evaluates as its own.  Here every thread evaluates F, G, H of its own
-// two rows ONCE, when the plane is first read (Q(k+2) in iteration k), carries them in the register queue (15
-// non-trivial components instead of H and the primitives) and publishes G of both rows and F of its first row to
-// shared memory for the iteration after; the one row below and the one column right of the thread tile, which no
-// thread owns, are evaluated by one designated warp each (scalar, 16 / 32 cells) one plane ahead as well.  A
-// neighbour's flux is the same function of the same tile values wherever it is evaluated -> the same bits as
-// k_fused_pair (tests).  Per warp and plane that removes 93 fp32-pipe cycles of 866 for 18 STS + 18 LDS.
-// -----------------------------------------------------------------------------------------------
-template <class V>
-struct FluxQ {   // F, G, H (indexed family) of one state, non-trivial components only:
-    V f[6];      //   F: MX MY MZ BY BZ EN          (F[RHO] = Q[MX], F[BX] = 0)
-    V g[5];      //   G: MY MZ BX BZ EN             (G[RHO] = Q[MY], G[BY] = 0, G[MX] = F[MY])
-    V h[4];      //   H: MZ BX BY EN                (H[RHO] = Q[MZ], H[BZ] = 0, H[MX] = F[MZ], H[MY] = G[MZ])
-};
-
-template <class V>
-__device__ __forceinline__ void flux_all(const V U[8], FluxQ<V>& X) {
-    const PrimT<V> s = make_prim(U);
-    V f[8], g[8], h[8];
-    flux_idx<DIR_X>(U, s, f);
-    flux_idx<DIR_Y>(U, s, g);
-    flux_idx<DIR_Z>(U, s, h);
-    X.f[0] = f[MX]; X.f[1] = f[MY]; X.f[2] = f[MZ]; X.f[3] = f[BY]; X.f[4] = f[BZ]; X.f[5] = f[EN];
-    X.g[0] = g[MY]; X.g[1] = g[MZ]; X.g[2] = g[BX]; X.g[3] = g[BZ]; X.g[4] = g[EN];
-    X.h[0] = h[MZ]; X.h[1] = h[BX]; X.h[2] = h[BY]; X.h[3] = h[EN];
-}
-template <class V>
-__device__ __forceinline__ void flux_expand(const V U[8], const FluxQ<V>& X, V f[8], V g[8], V h[8]) {
-    f[RHO] = U[MX]; f[MX] = X.f[0]; f[MY] = X.f[1]; f[MZ] = X.f[2]; f[BX] = vset<V>(0.0f); f[BY] = X.f[3]; f[BZ] = X.f[4]; f[EN] = X.f[5];
-    g[RHO] = U[MY]; g[MX] = X.f[1]; g[MY] = X.g[0]; g[MZ] = X.g[1]; g[BX] = X.g[2]; g[BY] = vset<V>(0.0f); g[BZ] = X.g[3]; g[EN] = X.g[4];
-    h[RHO] = U[MZ]; h[MX] = X.f[2]; h[MY] = X.g[1]; h[MZ] = X.h[0]; h[BX] = X.h[1]; h[BY] = X.h[2]; h[BZ] = vset<V>(0.0f); h[EN] = X.h[3];
-}
-
-template <int PATH, int TI>
-struct CarryGeo : PairGeo<PATH, TI> {
-    using B = PairGeo<PATH, TI>;
-    static constexpr int FXV = (TI + 1) * 32;        // component stride of the published x fluxes: thread rows 0..TI-1 (their
-                                                     // first row) + slot TI = the row below the thread tile
-    static constexpr int FXBUF = 6 * FXV;
-    static constexpr int GYP = 33;                   // row pitch of the published y fluxes: 32 lanes + the column right of the tile
-    static constexpr int GYV = B::NR * GYP;
-    static constexpr int GYBUF = 6 * GYV;
-    static constexpr int NXBUF = 4;                  // split-phase Qint exchange (see SplitGeo)
-    static constexpr size_t SMEM = B::NSTAGE * B::STAGE_BYTES + (NXBUF * B::XBUF + 2 * FXBUF + 2 * GYBUF) * 4 + 128;
-};
-
-// Fluxes of plane k+2 (tile tq2) -> registers (Xn) and the NEXT plane's exchange buffers (fxn, gyn); predictor of plane
-// k+1 from the carried fluxes X1 and THIS plane's exchange buffers (fxc, gyc), which were filled one iteration ago.
-template <int PATH, int TI>
-__device__ __forceinline__ void carry_predict(const FusedArgs& A, const PairThread& T, int role, int gcol, bool hi, const float* tq1,
-                                              const float* tq2, const float* fxc, const float* gyc, float* fxn, float* gyn,
-                                              uint64_t* ybar, const float2 (&q0)[8], const float2 (&q1)[8], float2 (&qn)[8],
-                                              const FluxQ<float2>& X1, FluxQ<float2>& Xn, float2 (&qip)[8]) {
-    using G = CarryGeo<PATH, TI>;
-    const Params& P = A.P;
-    constexpr int VS = G::TR * kTC;   // variable stride inside a tile
-    const FlagT<float2> right = {T.right(), T.right()};
-    const int lane = T.xs & 31, ti = T.xs >> 5;
-    // plane k+2 first (the flux evaluation wants it first), then this plane's neighbour values: their latency hides under
-    // the flux evaluation
-#pragma unroll
-    for (int v = 0; v < 8; ++v) qn[v] = make_float2(tq2[v * VS + T.own], tq2[v * VS + T.own + kTC]);
-    float xlast[8], xfirst[8], fl[8];
-    float2 yp[8], ym[8], gy[8];
-#pragma unroll
-    for (int v = 0; v < 8; ++v) {
-        xlast[v] = tq1[v * VS + T.own + 2 * kTC];                       // Q(k+1) one row below the thread's rows
-        yp[v] = make_float2(tq1[v * VS + T.own + 1], tq1[v * VS + T.own + kTC + 1]);
-        if (PATH == IMHD_PATH_B) {
-            xfirst[v] = tq1[v * VS + T.own - kTC];                      // ... and one row above
-            ym[v] = make_float2(tq1[v * VS + T.own - 1], tq1[v * VS + T.own + kTC - 1]);
-        }
-    }
-    {   // F(Q(k+1)) of the row below (the first row of the next thread row, or slot TI) and G(Q(k+1)) one column right
-        const float* fp = fxc + (ti + 1) * 32 + lane;
-        const float* gp = gyc + (2 * ti) * G::GYP + lane + 1;
-        fl[RHO] = xlast[MX]; fl[BX] = 0.0f;
-        fl[MX] = fp[0 * G::FXV]; fl[MY] = fp[1 * G::FXV]; fl[MZ] = fp[2 * G::FXV];
-        fl[BY] = fp[3 * G::FXV]; fl[BZ] = fp[4 * G::FXV]; fl[EN] = fp[5 * G::FXV];
-        gy[RHO] = make_float2(yp[MY].x, yp[MY].y); gy[BY] = make_float2(0.0f, 0.0f);
-        gy[MX] = make_float2(gp[0 * G::GYV], gp[0 * G::GYV + G::GYP]);
-        gy[MY] = make_float2(gp[1 * G::GYV], gp[1 * G::GYV + G::GYP]);
-        gy[MZ] = make_float2(gp[2 * G::GYV], gp[2 * G::GYV + G::GYP]);
-        gy[BX] = make_float2(gp[3 * G::GYV], gp[3 * G::GYV + G::GYP]);
-        gy[BZ] = make_float2(gp[4 * G::GYV], gp[4 * G::GYV + G::GYP]);
-        gy[EN] = make_float2(gp[5 * G::GYV], gp[5 * G::GYV + G::GYP]);
-    }
-    // ---- plane k+2: its fluxes, and what the neighbours will want of them next iteration ---------------------------
-    flux_all(qn, Xn);
-    {
-        float* fp = fxn + ti * 32 + lane;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) fp[c * G::FXV] = Xn.f[c].x;
-        float* gp = gyn + (2 * ti) * G::GYP + lane;
-        gp[0 * G::GYV] = Xn.f[1].x; gp[0 * G::GYV + G::GYP] = Xn.f[1].y;          // G[MX] = F[MY]
-#pragma unroll
-        for (int c = 0; c < 5; ++c) { gp[(c + 1) * G::GYV] = Xn.g[c].x; gp[(c + 1) * G::GYV + G::GYP] = Xn.g[c].y; }
-    }
-    if (role) {  // warp-uniform: the last warp owns the row below the thread tile, warp 0 the column to its right
-        float u[8], t[8];
-        const int off = role == 1 ? T.own + 2 * kTC : gcol;
-#pragma unroll
-        for (int v = 0; v < 8; ++v) u[v] = tq2[v * VS + off];
-        const Prim s = make_prim(u);
-        if (role == 1) {
-            flux_idx<DIR_X>(u, s, t);
-            float* fp = fxn + TI * 32 + lane;
-            fp[0 * G::FXV] = t[MX]; fp[1 * G::FXV] = t[MY]; fp[2 * G::FXV] = t[MZ];
-            fp[3 * G::FXV] = t[BY]; fp[4 * G::FXV] = t[BZ]; fp[5 * G::FXV] = t[EN];
-        } else {
-            flux_idx<DIR_Y>(u, s, t);
-            float* gp = gyn + (lane & (G::NR - 1)) * G::GYP + 32;   // lanes >= NR repeat rows 0.. with the same values
-            gp[0 * G::GYV] = t[MX]; gp[1 * G::GYV] = t[MY]; gp[2 * G::GYV] = t[MZ];
-            gp[3 * G::GYV] = t[BX]; gp[4 * G::GYV] = t[BZ]; gp[5 * G::GYV] = t[EN];
-        }
-    }
-    mbar_arrive(ybar);
-    // ---- predictor of plane k+1 -----------------------------------------------------------------------------
-    {
-        float2 f[8], g[8], h1[8], hn[8], dF[8], xsum[8];
-        {
-            float2 fdum[8], gdum[8];
-            flux_expand(q1, X1, f, g, h1);
-            flux_expand(qn, Xn, fdum, gdum, hn);
-        }
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-            dF[v].x = T.bottom(0) ? -f[v].x : f[v].y - f[v].x;   // the second row's flux is the first row's i+1 neighbour
-            dF[v].y = T.bottom(1) ? -f[v].y : fl[v] - f[v].y;
-            if (PATH == IMHD_PATH_B) xsum[v] = make_float2(q1[v].y + xfirst[v], xlast[v] + q1[v].x);
-        }
-        qint_combine<PATH, float2>(q1, dF, g, gy, h1, hn, xsum, ym, yp, q0, qn, {T.bottom(0), T.bottom(1)}, right,
-                                   {T.interior_i(0) && T.interior_j(), T.interior_i(1) && T.interior_j()}, P, qip);
-    }
-    if (__builtin_expect(hi, 0)) {  // the plane above the slab comes from the neighbour (or is the periodic image): once per slab
-        float a[8], b[8];
-        ldg8(A.qhi, (long long)min(T.i0, P.Nx - 1) * P.Ny + T.jc, P.plane, a);
-        ldg8(A.qhi, (long long)min(T.i0 + 1, P.Nx - 1) * P.Ny + T.jc, P.plane, b);
-#pragma unroll
-        for (int v = 0; v < 8; ++v) qip[v] = make_float2(a[v], b[v]);
-    }
-}
-
 template <int PATH, int TI, int MINB = 1>
-__global__ void __launch_bounds__(TI * 32, MINB) k_fused_carry(const FusedArgs A, const __grid_constant__ CUtensorMap tmap) {
-    using G = CarryGeo<PATH, TI>;
+__global__ void __launch_bounds__(TI * 32, MINB) k_fused_split(const FusedArgs A, const __grid_constant__ CUtensorMap tmap) {
+    using G = SplitGeo<PATH, TI>;
     constexpr int NS = G::NSTAGE;
-    static_assert(G::NR <= 32 && (G::NR & (G::NR - 1)) == 0, "the column right of the tile is evaluated by the lanes of one warp");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);                       // [NS][8][TR][kTC]
     float* xch = tiles + NS * G::STAGE_FLOATS;                                // [2][first,last][8][TI][32]  Qint exchange
-    float* fxb = xch + G::NXBUF * G::XBUF;                                    // [2][6][TI+1][32]  F(Q), first rows + the row below the tile
-    float* gyb = fxb + 2 * G::FXBUF;                                          // [2][6][NR][33]    G(Q), all rows + the column right of the tile
-    uint64_t* full = reinterpret_cast<uint64_t*>(gyb + 2 * G::GYBUF);         // [NS] tile landed
+    uint64_t* full = reinterpret_cast<uint64_t*>(xch + G::NXBUF * G::XBUF);   // [NS] tile landed
     uint64_t* xbar = full + NS;                                               // [2] Qint rows of a plane published (even / odd planes)
-    uint64_t* ybar = xbar + 2;                                                // [1] fluxes of a plane published
 
     const Params& P = A.P;
     const int lane = threadIdx.x, ti = threadIdx.y;
@@ -1179,135 +1017,13 @@ __global__ void __launch_bounds__(TI * 32, MINB) k_fused_carry(const FusedArgs A
     T.xsp = min(ti + 1, TI - 1) * 32 + lane;
     T.i0 = i0;
     T.jc = min(j, P.Ny - 1);
-    int role = ti == TI - 1 ? 1 : (ti == 0 ? 2 : 0);
-    int gcol = ((lane & (G::NR - 1)) + 1) * kTC + (jb - 1 - c0) + 33;   // tile offset of (thread-tile row lane, the column right of the tile)
-    keep(T.rows); keep(T.lanes); keep(T.own); keep(T.xs); keep(T.xsm); keep(T.xsp); keep(role); keep(gcol);
+    keep(T.rows); keep(T.lanes); keep(T.own); keep(T.xs); keep(T.xsm); keep(T.xsp);
 
-    const int ka = A.kfrom + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kto);
-    const bool first = ka == A.ka0;  // the plane below is the slab's qint_lo; otherwise re-derive it in a warm-up plane
-    const int ks = first ? ka - 1 : ka - 2;
-    const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
-    const int klast = kb + 1;  // last plane any iteration reads
-
-    auto issue = [&](int plane, int stage) {  // producer only
-        const int kc = min(max(plane, A.kmin), A.kmax) - A.kbase;
-        mbar_expect_tx(&full[stage], G::STAGE_BYTES);
-        tma_load_tile(tiles + stage * G::STAGE_FLOATS, &tmap, &full[stage], c0, ib - 1, kc);
-    };
-
-    if (producer) {
-        for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
-        mbar_init(&xbar[0], TI * 32);
-        mbar_init(&xbar[1], TI * 32);
-        mbar_init(&ybar[0], TI * 32);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async;" ::: "memory");
-    }
-    __syncthreads();
-    if (producer)
-        for (int s = 0; s < NS; ++s) issue(ks + s, s);
-
-    float2 qa[8], qb[8], qc[8], ia[8], ib_[8], ic[8];
-    FluxQ<float2> Xb, Xc;
-    constexpr int VS = G::TR * kTC;
-    mbar_wait(&full[0], 0);
-    mbar_wait(&full[1], 0);
-#pragma unroll
-    for (int v = 0; v < 8; ++v) {
-        qa[v] = make_float2(tiles[v * VS + T.own], tiles[v * VS + T.own + kTC]);
-        qb[v] = make_float2(tiles[G::STAGE_FLOATS + v * VS + T.own], tiles[G::STAGE_FLOATS + v * VS + T.own + kTC]);
-        ia[v] = make_float2(1.0f, 1.0f);
-        ib_[v] = make_float2(1.0f, 1.0f);
-    }
-    if (first) {  // Qint(ka-1); rows beyond the domain read the last row (they never produce output)
-        float a[8], b[8];
-        ldg8(A.qlo, (long long)min(i0, P.Nx - 1) * P.Ny + T.jc, P.plane, a);
-        ldg8(A.qlo, (long long)min(i0 + 1, P.Nx - 1) * P.Ny + T.jc, P.plane, b);
-#pragma unroll
-        for (int v = 0; v < 8; ++v) ib_[v] = make_float2(a[v], b[v]);
-    }
-    {   // fluxes of plane ks+1 and their exchange entries, as the loop body produces them for every later plane
-        const float* tq = tiles + G::STAGE_FLOATS;
-        flux_all(qb, Xb);
-        float* fp = fxb + ti * 32 + lane;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) fp[c * G::FXV] = Xb.f[c].x;
-        float* gp = gyb + (2 * ti) * G::GYP + lane;
-        gp[0 * G::GYV] = Xb.f[1].x; gp[0 * G::GYV + G::GYP] = Xb.f[1].y;
-#pragma unroll
-        for (int c = 0; c < 5; ++c) { gp[(c + 1) * G::GYV] = Xb.g[c].x; gp[(c + 1) * G::GYV + G::GYP] = Xb.g[c].y; }
-        if (role) {
-            float u[8], t[8];
-            const int off = role == 1 ? T.own + 2 * kTC : gcol;
-#pragma unroll
-            for (int v = 0; v < 8; ++v) u[v] = tq[v * VS + off];
-            const Prim s = make_prim(u);
-            if (role == 1) {
-                flux_idx<DIR_X>(u, s, t);
-                float* fq = fxb + TI * 32 + lane;
-                fq[0 * G::FXV] = t[MX]; fq[1 * G::FXV] = t[MY]; fq[2 * G::FXV] = t[MZ];
-                fq[3 * G::FXV] = t[BY]; fq[4 * G::FXV] = t[BZ]; fq[5 * G::FXV] = t[EN];
-            } else {
-                flux_idx<DIR_Y>(u, s, t);
-                float* gq = gyb + (lane & (G::NR - 1)) * G::GYP + 32;
-                gq[0 * G::GYV] = t[MX]; gq[1 * G::GYV] = t[MY]; gq[2 * G::GYV] = t[MZ];
-                gq[3 * G::GYV] = t[BX]; gq[4 * G::GYV] = t[BZ]; gq[5 * G::GYV] = t[EN];
-            }
-        }
-    }
-
-    mbar_arrive(&ybar[0]);
-    // output pointer of the first row at plane ks; stores are predicated off below plane ka
-    float* outp = A.Qout + (long long)(ks - A.kbase) * P.plane + (long long)i0 * P.Ny + T.jc;
-    int xr = 0, fsel = 0, gsel = 0;   // exchange buffers of this plane: Qint rows (index, four buffers), fluxes (floats, two)
-#pragma unroll
-    for (int v = 0; v < 8; ++v) {
-        xch[v * TI * 32 + T.xs] = ib_[v].x;
-        xch[(8 + v) * TI * 32 + T.xs] = ib_[v].y;
-    }
-    mbar_arrive(&xbar[0]);
-    uint32_t xpar = 0, ypar = 0;
-    int s2 = 2;          // stage of plane k+2
-    uint32_t par = 0x3;  // bit s = parity of the next wait on stage s: stages 0,1 were waited once in the prologue
-#pragma unroll 1
-    for (int k = ks; k < kb; ++k) {
-        const int s1 = (s2 + NS - 1) % NS, s0 = (s2 + NS - 2) % NS;
-        const float* xq = xch + xr * G::XBUF;   // Qint(k) rows, stored during the previous iteration
-        const int xb = xr & 1;
-        xr = (xr + 1) & 3;
-        const float* fxc = fxb + fsel;
-        const float* gyc = gyb + gsel;
-        fsel ^= G::FXBUF; gsel ^= G::GYBUF;
-        mbar_wait(&full[s2], (par >> s2) & 1u);
-        par ^= 1u << s2;
-        // the neighbours' fluxes of plane k+1: published early in their iteration k-1.  Passing this wait also means every
-        // warp has read the fluxes of plane k (it does so before it publishes), whose buffers this iteration overwrites.
-        mbar_wait(&ybar[0], ypar);
-        ypar ^= 1u;
-        carry_predict<PATH, TI>(A, T, role, gcol, k + 1 == A.hi_plane, tiles + s1 * G::STAGE_FLOATS, tiles + s2 * G::STAGE_FLOATS, fxc, gyc,
-                                fxb + fsel, gyb + gsel, ybar, qa, qb, qc, Xb, Xc, ic);
-        {
-            float* xn = xch + xr * G::XBUF;
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-                xn[v * TI * 32 + T.xs] = ic[v].x;
-                xn[(8 + v) * TI * 32 + T.xs] = ic[v].y;
-            }
-            mbar_arrive(&xbar[xb ^ 1]);
-        }
-        mbar_wait(&xbar[xb], (xpar >> xb) & 1u);
-        xpar ^= 1u << xb;
-        if (producer && k + NS <= klast) issue(k + NS, s0);
-        pair_correct<PATH, TI>(A, T, k >= ka, xq, qa, ia, ib_, ic, outp);
-        outp += P.plane;
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-            qa[v] = qb[v]; qb[v] = qc[v];
-            ia[v] = ib_[v]; ib_[v] = ic[v];
-        }
-        Xb = Xc;
-        s2 = (s2 + 1) % NS;
-    }
+    // One instantiation for every block.  A second one with the wall / edge selects folded away for interior blocks
+    // (W = false; 82 % of the blocks at 304 x 304) is bit-identical and measures SLOWER (1.604 vs 1.594 ms per step): the
+    // 68 FSEL it saves per warp and plane are worth 3.4 % when every block runs that body alone, but two 17 KB bodies in
+    // flight on neighbouring SMs cost more in instruction fetch (tools/experiments/README.md).
+    split_march<PATH, TI, true>(A, tmap, T, tiles, xch, full, xbar, i0, ib, c0);
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -1327,8 +1043,8 @@ constexpr int kStripRows = 6;   // at most this many compute rows
 #ifndef IMHD_STRIP_REGS
 #define IMHD_STRIP_REGS 168
 #endif
-template <int PATH, int REGS = IMHD_STRIP_REGS>
-__global__ void __maxnreg__(REGS) k_fused_strip(const FusedArgs A, const __grid_constant__ CUtensorMap tmap) {
+template <int PATH>
+__global__ void __maxnreg__(IMHD_STRIP_REGS) k_fused_strip(const FusedArgs A, const __grid_constant__ CUtensorMap tmap) {
     constexpr int O = Ring<PATH>::O;
     constexpr int WL = 32 - 2 * O;
     // The staging tile of a plane is ONE TMA box (12 columns x 32 rows x 8 variables, dense: row pitch 12 floats), four
@@ -1357,7 +1073,8 @@ __global__ void __maxnreg__(REGS) k_fused_strip(const FusedArgs A, const __grid_
     const int c0 = A.jstrip & ~3;                      // first column of the staging tile (16-byte aligned in every row)
     const int st_own = lane * PITCH + (A.jstrip - c0) + tj + 1;
 
-    const int ka = A.kfrom + blockIdx.z * A.chunk, kb = min(ka + A.chunk, A.kto);
+    int ka, kb;
+    chunk_range(A, blockIdx.z, ka, kb);
     const bool first = ka == A.ka0;
     const int ks = first ? ka - 1 : ka - 2;
     auto plane_off = [&](int k) -> long long {
@@ -1490,10 +1207,11 @@ __global__ void __launch_bounds__(128, 2) k_fused_wstrip(const FusedArgs A) {
     const Params& P = A.P;
     const int lane = threadIdx.x & 31;
     float* ring = ws_smem + (threadIdx.x >> 5) * (kWsNst * kWsStage);   // this warp's private staging ring
-    const int w = blockIdx.x * 4 + (threadIdx.x >> 5);      // warp tile: tile row bi, z chunk cz
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // warp tile: tile row bi, z chunk cz
     const int bi = w % A.ntile_i, cz = w / A.ntile_i;
-    const int ka = A.kfrom + cz * A.chunk, kb = min(ka + A.chunk, A.kto);
-    if (ka >= A.kto) return;                                 // warp-uniform
+    int ka, kb;
+    chunk_range(A, cz, ka, kb);
+    if (ka >= kb) return;                                    // warp-uniform: a warp beyond the last chunk
     const int r = lane >> 2, c = lane & 3;
     const int ib = bi * WI, t0 = 2 * r, i0 = ib + t0, j = A.jstrip + 1 + c;
     const int oi_lo = bi == 0 ? 0 : ib + 1, oi_hi = bi == A.ntile_i - 1 ? P.Nx : ib + WI + 1;
@@ -1806,7 +1524,7 @@ static int fill_args(FusedArgs& A, const float* Qin, float* Qout, const float* q
     A.qlo = qlo; A.qhi = qhi; A.qwrap = qwrap;
     A.hi_plane = min(A.k1, s->Nz - 1);
     A.corner_e = s->corner_e;
-    A.chunk = 0; A.ntile_i = A.ntile_j = 0; A.jstrip = 0;
+    A.chunk = A.clen = 0; A.ntile_i = A.ntile_j = 0; A.jstrip = 0;
     return 0;
 }
 
@@ -1852,18 +1570,48 @@ static PFN_cuTensorMapEncodeTiled get_encode() {
     return fn;
 }
 
-static int g_force_ldg = 0, g_no_strip = 0, g_force_strip = 0, g_kernel = 0, g_co_strip = 0, g_block_strip = 0;
+static int g_force_ldg = 0, g_no_strip = 0, g_force_strip = 0, g_no_under = 0, g_kernel = 0, g_block_strip = 0;
 extern "C" void imhd_set_kernel_variant(int flags) {
-    g_force_ldg = flags & 1; g_no_strip = (flags >> 1) & 1; g_force_strip = (flags >> 2) & 1; g_co_strip = (flags >> 3) & 1;
+    g_force_ldg = flags & 1; g_no_strip = (flags >> 1) & 1; g_force_strip = (flags >> 2) & 1; g_no_under = (flags >> 3) & 1;
     g_kernel = (flags >> 4) & 15; g_block_strip = (flags >> 8) & 1;
 }
 
-// Side stream of the co-resident remainder strip (one per device; the fork / launch / join triple is enqueued under the mutex).
+// ---- work that runs UNDER the path B marching kernel ------------------------------------------------------------------
+// A block of the path B marching kernel (8 warps x 208 registers, one block per SM) leaves 12288 registers, ~60 KB of shared
+// memory and -- being bound by its own dependency latency -- issue slots of its SM idle.  The small launches of a step that
+// depend only on the OLD state (the remainder strip: a latency chain of its own; the k = 0 face and the k = Nz-1 plane of
+// path B) are therefore forked onto a per-device side stream in blocks small enough to be co-resident with a marching block
+// (one 32-thread strip block of 228 registers per SM; 64-thread face blocks) and joined behind the marching kernel: they
+// cost the step their share of the issue slots instead of their own latency (0.12 ms of 1.64 at 304x304x592).
 namespace {
-struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
-SideStream g_side[64];
-std::mutex g_side_mu;
+struct UnderStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+UnderStream g_under[64];
+std::mutex g_under_mu;   // a fork or join is an event record + a stream wait on that event: one atomic pair per host thread
 }  // namespace
+
+static UnderStream* under_stream() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> g(g_under_mu);
+    UnderStream* u = &g_under[dev & 63];
+    if (!u->s) {
+        if (cudaStreamCreateWithFlags(&u->s, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&u->fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&u->join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            u->s = nullptr;
+            return nullptr;
+        }
+    }
+    return u;
+}
+// `to` continues after everything enqueued on `from` so far
+static int stream_follows(cudaStream_t to, cudaStream_t from, cudaEvent_t ev) {
+    std::lock_guard<std::mutex> g(g_under_mu);
+    IMHD_CUDA(cudaEventRecord(ev, from));
+    IMHD_CUDA(cudaStreamWaitEvent(to, ev, 0));
+    return 0;
+}
 
 // 4-D view (j, i, plane, variable) of a state array for the tile loads of the TMA kernel.
 static bool make_tile_map(CUtensorMap* map, const FusedArgs& A, int nplanes, int tile_rows, int tile_cols = kTC,
@@ -1893,7 +1641,14 @@ static int ensure_smem(K kernel, size_t bytes, unsigned long long& done_mask) {
     return 0;
 }
 
+// A launch over two plane ranges arrives with chunk (the distance between the ranges' first planes) and clen (their common
+// length) set by step_ranges and runs one z-chunk per range; otherwise the launcher picks the chunk length.
+static bool two_ranges(const FusedArgs& A) { return A.clen > 0 && A.clen < A.chunk; }
+static int longest_range(const FusedArgs& A) { return two_ranges(A) ? A.clen : A.kto - A.kfrom; }
+static int count_chunks(const FusedArgs& A) { return two_ranges(A) ? 2 : (A.kto - A.kfrom + A.chunk - 1) / A.chunk; }
+
 static int pick_chunk(FusedArgs& A, int nz, long long tiles = 0, int blocks_per_sm = 1) {
+    if (two_ranges(A)) return 2;
     // z-chunks: one block per SM is resident (register-limited), so the launch runs in waves of `sms` blocks.  Pick the
     // chunk count that minimises  waves x (chunk length + warm-up)  -- i.e. fill the last wave -- with chunks long
     // enough to amortise the two warm-up planes (each costs about half a plane).
@@ -1915,7 +1670,7 @@ static int pick_chunk(FusedArgs& A, int nz, long long tiles = 0, int blocks_per_
     if (g_chunk_override > 0) chunk = g_chunk_override;
     if (chunk < 2) chunk = 2;
     if (chunk > nz) chunk = nz;
-    A.chunk = chunk;
+    A.chunk = A.clen = chunk;
     return (nz + chunk - 1) / chunk;
 }
 
@@ -1943,14 +1698,6 @@ struct SplitLaunch {
     static constexpr int BLOCKS_PER_SM = MINB;
     static auto kernel() { return k_fused_split<PATH, TI, MINB>; }
 };
-template <int PATH, int TI, int MINB = 1>
-struct CarryLaunch {
-    using G = CarryGeo<PATH, TI>;
-    static constexpr int THREAD_ROWS = TI;
-    static constexpr int BLOCKS_PER_SM = MINB;
-    static auto kernel() { return k_fused_carry<PATH, TI, MINB>; }
-};
-
 // ---- optional per-launch timing of the hot kernel (bench.py's roofline leg) ---------------------------------------------
 // When enabled, every launch of the marching kernel that covers >= 64 planes (+ its remainder strip) is bracketed by
 // a CUDA event pair on the launching stream; imhd_fused_timing_read sums them after the caller has synchronised.
@@ -2005,10 +1752,10 @@ static void timing_end(TimedLaunch* t, cudaStream_t st) {
 }
 
 template <int PATH, class L>
-static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, int nplanes_array, cudaStream_t st) {
+static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, int nplanes_array, cudaStream_t st, UnderStream* under) {
     using G = typename L::G;
     const Params& P = A.P;
-    const int nz = A.kto - A.kfrom;
+    const int nz = longest_range(A);
     const int ni = PATH == IMHD_PATH_A ? P.Nx - 1 : P.Nx - 2, nj = PATH == IMHD_PATH_A ? P.Ny - 1 : P.Ny - 2;
     A.ntile_i = (ni + G::WI - 1) / G::WI;
     A.ntile_j = (nj + G::WJ - 1) / G::WJ;
@@ -2024,33 +1771,14 @@ static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, int nplanes_array, 
         grid_j = nj / G::WJ;
         A.ntile_j = grid_j + 1;  // no hot-kernel tile is the last one: none widens its window to the domain edge
     }
-    const int nchunk = pick_chunk(A, nz, (long long)A.ntile_i * grid_j, L::BLOCKS_PER_SM);
+    pick_chunk(A, nz, (long long)A.ntile_i * grid_j, L::BLOCKS_PER_SM);
+    const int nchunk = count_chunks(A);
     static unsigned long long done = 0;
     if (int e = ensure_smem(L::kernel(), G::SMEM, done)) return e;
     TimedLaunch* timed = timing_begin(A, nz, st);
-    // Co-resident strip: a hot block leaves 10240 registers and ~100 KB of shared memory of its SM idle, and the strip is a
-    // latency chain (IPC 0.7) -- so the strip runs UNDER the hot kernel instead of after it: one 128-thread block per SM at
-    // an 80-register cap, on a high-priority side stream forked in front of the hot launch and joined behind it.
-    const bool co = strip && g_co_strip && L::BLOCKS_PER_SM == 1;
-    SideStream* side = nullptr;
-    std::unique_lock<std::mutex> side_lock;
-    if (co) {
-        int dev = 0;
-        IMHD_CUDA(cudaGetDevice(&dev));
-        side_lock = std::unique_lock<std::mutex>(g_side_mu);
-        side = &g_side[dev & 63];
-        if (!side->s) {
-            int lo = 0, hi = 0;
-            IMHD_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            IMHD_CUDA(cudaStreamCreateWithPriority(&side->s, cudaStreamNonBlocking, hi));
-            IMHD_CUDA(cudaEventCreateWithFlags(&side->fork, cudaEventDisableTiming));
-            IMHD_CUDA(cudaEventCreateWithFlags(&side->join, cudaEventDisableTiming));
-        }
-        IMHD_CUDA(cudaEventRecord(side->fork, st));
-    }
     L::kernel()<<<dim3(grid_j, A.ntile_i, nchunk), dim3(32, L::THREAD_ROWS), G::SMEM, st>>>(A, tmap);
     IMHD_LAUNCH_CHECK(1);
-    if (strip && strip_rows <= 4 && !g_block_strip && !co) {
+    if (strip && strip_rows <= 4 && !g_block_strip) {
         // warp-autonomous strip: one warp per 16-row x 4-column tile and z chunk, eight warps per SM
         FusedArgs S = A;
         constexpr int WIw = PATH == IMHD_PATH_A ? 15 : 14;
@@ -2059,17 +1787,29 @@ static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, int nplanes_array, 
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        int n = (8 * sms) / S.ntile_i;                        // one wave of warps
-        n = n > nz / 8 ? nz / 8 : n;
-        n = n < 1 ? 1 : n;
-        S.chunk = (nz + n - 1) / n;
-        if (g_chunk_override > 0) S.chunk = g_chunk_override;
-        S.chunk = S.chunk < 2 ? 2 : (S.chunk > nz ? nz : S.chunk);
-        const int warps = S.ntile_i * ((nz + S.chunk - 1) / S.chunk);
+        if (!two_ranges(A)) {   // (two ranges: one chunk per range, as the marching kernel)
+            int n = (8 * sms) / S.ntile_i;                    // one wave of warps: two 4-warp blocks per SM (230 registers)
+            n = n > nz / 8 ? nz / 8 : n;
+            n = n < 1 ? 1 : n;
+            S.chunk = (nz + n - 1) / n;
+            if (g_chunk_override > 0) S.chunk = g_chunk_override;
+            S.chunk = S.chunk < 2 ? 2 : (S.chunk > nz ? nz : S.chunk);
+            S.clen = S.chunk;
+        }
+        const int warps = S.ntile_i * count_chunks(S);
         static unsigned long long wdone = 0;
         if (int e = ensure_smem(k_fused_wstrip<PATH>, kWsSmem, wdone)) return e;
-        k_fused_wstrip<PATH><<<(warps + 3) / 4, 128, kWsSmem, st>>>(S);
-        IMHD_LAUNCH_CHECK(1);
+        if (under && L::BLOCKS_PER_SM == 1) {
+            // one-warp blocks on the side stream, launched after the marching kernel: one fits beside each marching block
+            k_fused_wstrip<PATH><<<warps, 32, kWsSmem / 4, under->s>>>(S);
+            IMHD_LAUNCH_CHECK(1);
+            if (timed) {   // the bracket of the roofline leg covers the strip
+                if (int e = stream_follows(st, under->s, under->join)) return e;
+            }
+        } else {
+            k_fused_wstrip<PATH><<<(warps + 3) / 4, 128, kWsSmem, st>>>(S);
+            IMHD_LAUNCH_CHECK(1);
+        }
     } else if (strip) {
         FusedArgs S = A;
         constexpr int WL = 32 - 2 * O;
@@ -2079,12 +1819,14 @@ static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, int nplanes_array, 
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         int n = (3 * sms + S.ntile_i - 1) / S.ntile_i;      // a few small blocks per SM
-        if (co) n = sms / S.ntile_i;                        // co-resident: one block per SM, all resident from the start
         n = n > nz / 8 ? nz / 8 : n;
         n = n < 1 ? 1 : n;
-        S.chunk = (nz + n - 1) / n;
-        if (g_chunk_override > 0) S.chunk = g_chunk_override;
-        S.chunk = S.chunk < 2 ? 2 : (S.chunk > nz ? nz : S.chunk);
+        if (!two_ranges(A)) {
+            S.chunk = (nz + n - 1) / n;
+            if (g_chunk_override > 0) S.chunk = g_chunk_override;
+            S.chunk = S.chunk < 2 ? 2 : (S.chunk > nz ? nz : S.chunk);
+            S.clen = S.chunk;
+        }
         constexpr size_t strip_smem = (2 * 8 * kStripRows * 32 + 4 * 8 * 32 * kStripCols) * sizeof(float) + 64;
         static unsigned long long sdone = 0;
         if (int e = ensure_smem(k_fused_strip<PATH>, strip_smem, sdone)) return e;
@@ -2093,51 +1835,38 @@ static int launch_tma(FusedArgs& A, const CUtensorMap& tmap, int nplanes_array, 
         // 128-byte promotion (and, measured, "none") fetch 277 MB -- for 46 MB needed.  The kernel's duration does not
         // depend on it (nor on cp.async vs TMA staging, nor on its register cap): see tools/experiments/README.md.
         if (!make_tile_map(&smap, A, nplanes_array, 32, kStripCols, CU_TENSOR_MAP_L2_PROMOTION_L2_64B)) { set_error("remainder strip: tensor map"); return IMHD_E_STATE; }
-        if (co) {
-            static unsigned long long cdone = 0;
-            if (int e = ensure_smem(k_fused_strip<PATH, 80>, strip_smem, cdone)) return e;
-            IMHD_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
-            k_fused_strip<PATH, 80><<<dim3(S.ntile_i, 1, (nz + S.chunk - 1) / S.chunk), dim3(32, strip_rows), strip_smem, side->s>>>(S, smap);
-            IMHD_LAUNCH_CHECK(1);
-            IMHD_CUDA(cudaEventRecord(side->join, side->s));
-            IMHD_CUDA(cudaStreamWaitEvent(st, side->join, 0));
-        } else {
-            k_fused_strip<PATH><<<dim3(S.ntile_i, 1, (nz + S.chunk - 1) / S.chunk), dim3(32, strip_rows), strip_smem, st>>>(S, smap);
-            IMHD_LAUNCH_CHECK(1);
-        }
+        k_fused_strip<PATH><<<dim3(S.ntile_i, 1, count_chunks(S)), dim3(32, strip_rows), strip_smem, st>>>(S, smap);
+        IMHD_LAUNCH_CHECK(1);
     }
     timing_end(timed, st);
     return 0;
 }
 
 template <int PATH>
-static int launch_fused(FusedArgs& A, int nplanes_array, cudaStream_t st) {
+static int launch_fused(FusedArgs& A, int nplanes_array, cudaStream_t st, UnderStream* under) {
     const Params& P = A.P;
-    const int nz = A.kto - A.kfrom;
+    const int nz = longest_range(A);
     if (nz <= 0) return 0;
     CUtensorMap tmap;
     // kernel choice (imhd_set_kernel_variant bits 4..7): 0 = default
     switch (g_kernel) {
         case 1:
-            if (make_tile_map(&tmap, A, nplanes_array, TmaGeo<PATH, 16>::TR)) return launch_tma<PATH, OneRowLaunch<PATH, 16>>(A, tmap, nplanes_array, st);
+            if (make_tile_map(&tmap, A, nplanes_array, TmaGeo<PATH, 16>::TR)) return launch_tma<PATH, OneRowLaunch<PATH, 16>>(A, tmap, nplanes_array, st, under);
             break;
         case 2:  // the 8-warp tile for either path
-            if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, PairLaunch<PATH, 8>>(A, tmap, nplanes_array, st);
+            if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, PairLaunch<PATH, 8>>(A, tmap, nplanes_array, st, under);
             break;
         case 4:  // split-phase exchange barrier on the 8-warp tile
-            if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, SplitLaunch<PATH, 8>>(A, tmap, nplanes_array, st);
-            break;
-        case 3:  // carried fluxes on the 8-warp tile
-            if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, CarryLaunch<PATH, 8>>(A, tmap, nplanes_array, st);
+            if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, SplitLaunch<PATH, 8>>(A, tmap, nplanes_array, st, under);
             break;
         default:
             // Path B: 8 warps x 2 rows = a 16x32 tile, one block per SM (its two-row ring makes smaller tiles too wasteful:
             // 4-warp tiles, 2 or 3 blocks per SM, measure 30.3 / 28.2 GLUPS against 32.0).  Path A: one ring row and ~170
             // registers suffice, so three INDEPENDENT 4-warp blocks per SM (8x32 tiles, 12 warps) win: 50.6 against 44.5.
             if (PATH == IMHD_PATH_A) {
-                if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 4>::TR)) return launch_tma<PATH, PairLaunch<PATH, 4, 3>>(A, tmap, nplanes_array, st);
+                if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 4>::TR)) return launch_tma<PATH, PairLaunch<PATH, 4, 3>>(A, tmap, nplanes_array, st, under);
             } else {
-                if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, SplitLaunch<PATH, 8>>(A, tmap, nplanes_array, st);
+                if (make_tile_map(&tmap, A, nplanes_array, PairGeo<PATH, 8>::TR)) return launch_tma<PATH, SplitLaunch<PATH, 8>>(A, tmap, nplanes_array, st, under);
             }
             break;
     }
@@ -2148,7 +1877,8 @@ static int launch_fused(FusedArgs& A, int nplanes_array, cudaStream_t st) {
     const int ni = PATH == IMHD_PATH_A ? P.Nx - 1 : P.Nx - 2, nj = PATH == IMHD_PATH_A ? P.Ny - 1 : P.Ny - 2;
     A.ntile_i = (ni + WI - 1) / WI;
     A.ntile_j = (nj + WJ - 1) / WJ;
-    const int nchunk = pick_chunk(A, nz);
+    pick_chunk(A, nz);
+    const int nchunk = count_chunks(A);
     const size_t smem = 2 * 2 * 8 * TI * 32 * sizeof(float);
     static unsigned long long done = 0;
     if (int e = ensure_smem(k_fused_step_ldg<PATH, TI>, smem, done)) return e;
@@ -2157,17 +1887,30 @@ static int launch_fused(FusedArgs& A, int nplanes_array, cudaStream_t st) {
     return 0;
 }
 
-// Output planes [kfrom, kto) of the slab only (global indices, clipped to the owned range).  Any split of the owned
-// range into such calls writes the same bits as one imhd_step_fused call; the slab solver launches the planes next
-// to the slab ends first so their exchange overlaps the interior launch.
-extern "C" int imhd_step_fused_planes(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
-                                      const float* qint_wrap, const imhd_slab* s, int kfrom, int kto, void* stream) {
+// Output planes [kfrom, kmid1) and [kmid2, kto) of the slab (global indices, clipped to the owned range; kmid1 == kmid2: one
+// range).  Any split of the owned range into such calls writes the same bits as one imhd_step_fused call; the slab solver
+// launches the planes next to BOTH slab ends first so their exchange overlaps the interior launch -- in ONE launch of the
+// marching kernel when the two ranges hold the same number of its planes (at most kMaxEndPlanes), else in two.
+constexpr int kMaxEndPlanes = 32;
+static int step_ranges(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi, const float* qint_wrap,
+                       const imhd_slab* s, int kfrom, int kmid1, int kmid2, int kto, void* stream) {
     FusedArgs A;
     if (int e = fill_args(A, Qin, Qout, qint_lo, qint_hi, qint_wrap, s)) return e;
     kfrom = max(kfrom, A.k0); kto = min(kto, A.k1);
+    kmid1 = min(max(kmid1, kfrom), kto); kmid2 = min(max(kmid2, kmid1), kto);
     if (kfrom >= kto) return 0;
-    A.kfrom = max(kfrom, A.ka0); A.kto = min(kto, A.kb0);
+    if (kmid1 < kmid2 && kfrom < kmid1 && kmid2 < kto) {   // two non-empty ranges with a gap between them
+        const int a0 = max(kfrom, A.ka0), a1 = min(kmid1, A.kb0), b0 = max(kmid2, A.ka0), b1 = min(kto, A.kb0);   // marching planes
+        const bool one_launch = a1 - a0 == b1 - b0 && a1 - a0 >= 1 && a1 - a0 <= kMaxEndPlanes && b0 > a1;
+        if (!one_launch) {
+            if (int e = step_ranges(Qin, Qout, qint_lo, qint_hi, qint_wrap, s, kfrom, kmid1, kmid1, kmid1, stream)) return e;
+            return step_ranges(Qin, Qout, qint_lo, qint_hi, qint_wrap, s, kmid2, kto, kto, kto, stream);
+        }
+        A.chunk = b0 - a0;
+        A.clen = a1 - a0;
+    }
     const bool do_front = kfrom == 0, do_back = kto == s->Nz;
+    A.kfrom = max(kfrom, A.ka0); A.kto = min(kto, A.kb0);
     if (Qin == Qout) { set_error("imhd_step_fused: Qin and Qout must be distinct buffers"); return IMHD_E_INVALID; }
     if (!qint_lo || !qint_hi || (s->path == IMHD_PATH_B && s->k0 == 0 && !qint_wrap)) {
         set_error("imhd_step_fused: missing predictor plane (qint_lo=%p qint_hi=%p qint_wrap=%p)", (const void*)qint_lo,
@@ -2178,7 +1921,7 @@ extern "C" int imhd_step_fused_planes(const float* Qin, float* Qout, const float
     const Params& P = A.P;
     const unsigned pb = (unsigned)((P.plane + 255) / 256);
     if (s->path == IMHD_PATH_A) {
-        if (int e = launch_fused<IMHD_PATH_A>(A, s->nzl + 2 * (s->ghosts ? 1 : 0), st)) return e;
+        if (int e = launch_fused<IMHD_PATH_A>(A, s->nzl + 2 * (s->ghosts ? 1 : 0), st, nullptr)) return e;
         if (A.k0 == 0 && A.k1 == P.Nz && do_back) {  // PBCs on one GPU; across slabs the ghost exchange carries this plane
             k_plane_copy<<<pb, 256, 0, st>>>(Qout, (long long)(0 - A.kbase) * P.plane, (long long)(P.Nz - 1 - A.kbase) * P.plane,
                                              P.plane, A.vs);
@@ -2186,16 +1929,34 @@ extern "C" int imhd_step_fused_planes(const float* Qin, float* Qout, const float
         }
         return 0;
     }
-    if (int e = launch_fused<IMHD_PATH_B>(A, s->nzl + 2 * (s->ghosts ? 1 : 0), st)) return e;
+    // a launch long enough for the remainder strip (the same bound) carries its small launches under the marching kernel
+    UnderStream* under = !g_no_under && !two_ranges(A) && A.kto - A.kfrom >= 64 ? under_stream() : nullptr;
+    if (under)
+        if (int e = stream_follows(under->s, st, under->fork)) return e;
+    if (int e = launch_fused<IMHD_PATH_B>(A, s->nzl + 2 * (s->ghosts ? 1 : 0), st, under)) return e;
+    cudaStream_t small = under ? under->s : st;
     if (do_front) {
-        k_front_plane_B<<<dim3((P.Ny + 31) / 32, (P.Nx + 7) / 8), dim3(32, 8), 0, st>>>(A);
+        if (under) k_front_plane_B<<<dim3((P.Ny + 31) / 32, (P.Nx + 1) / 2), dim3(32, 2), 0, small>>>(A);
+        else       k_front_plane_B<<<dim3((P.Ny + 31) / 32, (P.Nx + 7) / 8), dim3(32, 8), 0, small>>>(A);
         IMHD_LAUNCH_CHECK(1);
     }
     if (do_back) {
-        k_back_plane_B<<<pb, 256, 0, st>>>(A);
+        k_back_plane_B<<<pb, 256, 0, small>>>(A);
         IMHD_LAUNCH_CHECK(1);
     }
+    if (under)
+        if (int e = stream_follows(st, under->s, under->join)) return e;
     return 0;
+}
+
+extern "C" int imhd_step_fused_planes(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
+                                      const float* qint_wrap, const imhd_slab* s, int kfrom, int kto, void* stream) {
+    return step_ranges(Qin, Qout, qint_lo, qint_hi, qint_wrap, s, kfrom, kto, kto, kto, stream);
+}
+
+extern "C" int imhd_step_fused_ends(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
+                                    const float* qint_wrap, const imhd_slab* s, int kfrom, int kmid1, int kmid2, int kto, void* stream) {
+    return step_ranges(Qin, Qout, qint_lo, qint_hi, qint_wrap, s, kfrom, kmid1, kmid2, kto, stream);
 }
 
 extern "C" int imhd_step_fused(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,

@@ -7,7 +7,7 @@
 //     imhd_create_multi   every slab in this process (one per device; NCCL communicators from ncclCommInitAll)
 //     imhd_create_slab    one slab per process (torchrun: one process per GPU; communicator from a shared unique id)
 // Both are the same code: per step and slab
-//   1. the fused kernel on the planes next to the two slab ends (imhd_step_fused_planes, EDGE planes each), an event,
+//   1. the fused kernel on the planes next to the two slab ends (imhd_step_fused_ends: ONE launch, EDGE planes each), an event,
 //      then the interior planes -- all on the slab's main stream;
 //   2. on the slab's side stream, under the interior launch: the new end planes go to the neighbours' ghost planes
 //      (for path A the plane the last slab sends up is the periodic copy Q[.,.,0] <- Q[.,.,Nz-1],
@@ -486,10 +486,12 @@ int eng_step(Engine* e, int nsteps) {
                 if (int rc = imhd_step_fused_planes(sl.Q[in], sl.Q[out], lo, hi, wrap, &sl.desc, k0, k1, sl.main)) return rc;
                 continue;
             }
-            if (int rc = imhd_step_fused_planes(sl.Q[in], sl.Q[out], lo, hi, wrap, &sl.desc, k0, k0 + E, sl.main)) return rc;
-            if (int rc = imhd_step_fused_planes(sl.Q[in], sl.Q[out], lo, hi, wrap, &sl.desc, k1 - E, k1, sl.main)) return rc;
+            // both ends hold E planes of the marching kernel (plane 0, and plane Nz-1 of path B, have kernels of their own and
+            // do not count): equal ranges go out as ONE launch
+            const int e0 = k0 + E + (k0 == 0 ? 1 : 0), e1 = k1 - E - (k1 == e->Nz && e->path == IMHD_PATH_B ? 1 : 0);
+            if (int rc = imhd_step_fused_ends(sl.Q[in], sl.Q[out], lo, hi, wrap, &sl.desc, k0, e0, e1, k1, sl.main)) return rc;
             IMHD_CUDA(cudaEventRecord(sl.ev_edges, sl.main));
-            if (int rc = imhd_step_fused_planes(sl.Q[in], sl.Q[out], lo, hi, wrap, &sl.desc, k0 + E, k1 - E, sl.main)) return rc;
+            if (int rc = imhd_step_fused_planes(sl.Q[in], sl.Q[out], lo, hi, wrap, &sl.desc, e0, e1, sl.main)) return rc;
             IMHD_CUDA(cudaStreamWaitEvent(sl.side, sl.ev_edges, 0));
         }
         if (!e->overlap) {

@@ -188,6 +188,14 @@ def step_fused_planes(Qin, Qout, qint_lo, qint_hi, qint_wrap, slab: Slab, kfrom:
                                    kfrom, kto, _stream()))
 
 
+def step_fused_ends(Qin, Qout, qint_lo, qint_hi, qint_wrap, slab: Slab, kfrom: int, kmid1: int, kmid2: int, kto: int):
+    """Output planes [kfrom, kmid1) and [kmid2, kto) of the slab in one launch (both slab ends of the multi-GPU loop)."""
+    L = _lib.load()
+    wrap = _dev(qint_wrap) if qint_wrap is not None else None
+    check(L.imhd_step_fused_ends(_dev(Qin), _dev(Qout, Qin.shape), _dev(qint_lo), _dev(qint_hi), wrap, C.byref(slab),
+                                 kfrom, kmid1, kmid2, kto, _stream()))
+
+
 def wall_energy_fixed_point(e: float, max_iter: int) -> float:
     return float(_lib.load().imhd_wall_energy_fixed_point(e, max_iter))
 

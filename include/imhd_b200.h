@@ -138,6 +138,11 @@ int imhd_step_fused(const float* Qin, float* Qout, const float* qint_lo, const f
 int imhd_step_fused_planes(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
                            const float* qint_wrap, const imhd_slab* s, int kfrom, int kto, void* stream);
 
+/* ... restricted to TWO plane ranges, [kfrom, kmid1) and [kmid2, kto), in ONE launch of the marching kernel: both slab
+ * ends at once (a launch over a few planes of one end fills 1.5 waves of thread blocks, both ends fill three). */
+int imhd_step_fused_ends(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
+                         const float* qint_wrap, const imhd_slab* s, int kfrom, int kmid1, int kmid2, int kto, void* stream);
+
 /* ---- CFL / stability scan (replaces the forked host scanner src/on-device/utils/compute_stability.cpp) ----------
  * One device pass over the owned planes of a slab state (same Q / imhd_slab conventions as imhd_step_fused; dt, dx,
  * dy, dz from the slab): LHS = (dt/dx)|l_x| + (dt/dy)|l_y| + (dt/dz)|l_z| per cell (:157-163) with |l_d| the
@@ -167,7 +172,9 @@ float imhd_wall_energy_fixed_point(float e, int max_iter);
 
 /* Test hooks: force the z-chunk length of the fused kernel (0 = automatic); kernel-variant flags: bit 0 forces the
  * plain-load variant instead of the TMA one, bit 1 disables the remainder-strip kernel, bit 2 uses it even for
- * plane ranges shorter than 64 (all give the same bits). */
+ * plane ranges shorter than 64, bit 8 selects the block-per-tile strip kernel instead of the warp-autonomous one, bits 4..7
+ * select the marching kernel (0 default, 1 one row per thread, 2 two rows per thread behind a block-wide barrier per plane,
+ * 4 two rows per thread with the split-phase exchange barrier on both pipelines).  All give the same bits. */
 void imhd_set_chunk(int planes);
 void imhd_set_kernel_variant(int flags);
 

@@ -270,8 +270,18 @@ def test_plane_range_launches_compose(imhd, torch, O, oracle_mod, dims, variant)
         ops.step_fused(Qin, ref, q0, q0, qw, s)
         for a, b in ((20, Nz), (0, 5), (5, 6), (6, 20)):   # out of order on purpose
             ops.step_fused_planes(Qin, out, q0, q0, qw, s, a, b)
+        # both ends in ONE launch (two plane ranges), then the interior: what the slab loop does; degenerate splits too
+        out2 = torch.full_like(Qin, float("nan"))
+        ops.step_fused_ends(Qin, out2, q0, q0, qw, s, 0, 4, Nz - 4, Nz)
+        ops.step_fused_ends(Qin, out2, q0, q0, qw, s, 4, 9, 9, Nz - 4)        # empty gap: one range
+        out3 = torch.full_like(Qin, float("nan"))
+        ops.step_fused_ends(Qin, out3, q0, q0, qw, s, 0, 1, Nz - 1, Nz)       # the two planes with their own rules only
+        ops.step_fused_ends(Qin, out3, q0, q0, qw, s, 1, 7, 11, Nz - 1)
+        ops.step_fused_planes(Qin, out3, q0, q0, qw, s, 7, 11)
         lib.imhd_set_kernel_variant(0)
         assert bits_equal(out.cpu().numpy(), ref.cpu().numpy()), path
+        assert bits_equal(out2.cpu().numpy(), ref.cpu().numpy()), path
+        assert bits_equal(out3.cpu().numpy(), ref.cpu().numpy()), path
 
 
 def test_fused_is_chunking_independent(imhd, torch, O, oracle_mod):
@@ -323,6 +333,29 @@ def test_remainder_strip_kernel_gives_the_same_bits(imhd, torch, O, oracle_mod, 
         finally:
             lib.imhd_set_kernel_variant(0)
         assert bits_equal(a, b) and bits_equal(a, c), path
+
+
+@pytest.mark.parametrize("variant", [8, 16, 32, 4 | 256, 4 | 32])
+def test_kernel_variants_give_the_same_bits(imhd, torch, O, oracle_mod, variant):
+    """The marching kernels the library carries -- default: split-phase exchange barrier + warp-autonomous strip, the strip and
+    the two z faces of path B running UNDER the marching kernel on a side stream; 8: everything on one stream; 16: one row
+    per thread; 32: two rows per thread behind a block-wide barrier per plane; 256: the block-per-tile (lanes along i) strip --
+    are the same arithmetic on the same values: identical bits, both pipelines, ragged grid with a remainder strip (Nz >= 66:
+    the side stream is only used for launches of 64 planes or more)."""
+    om = oracle_mod
+    lib = imhd._lib.load()
+    dims = (44, 64, 70)
+    g, d, Q0 = make_case(O, om, *dims, ic="bennett")
+    Q0 = Q0 + 0.01 * random_state(*dims, seed=5)
+    for path, D in paths(om):
+        try:
+            lib.imhd_set_kernel_variant(4)          # default kernels, strip on
+            a = run_fused(imhd, Q0, path, D, DT, d, 6)
+            lib.imhd_set_kernel_variant(variant)
+            b = run_fused(imhd, Q0, path, D, DT, d, 6)
+        finally:
+            lib.imhd_set_kernel_variant(0)
+        assert bits_equal(a, b), (path, variant)
 
 
 def test_fused_matches_granular_on_device(imhd, torch, O, oracle_mod):
