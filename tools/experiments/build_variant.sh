@@ -7,7 +7,7 @@ name=$1; shift
 src=${IMHD_FUSED_SRC:-imhd_fused.cu}
 out=../../tools/experiments/_build
 mkdir -p $out
-make -s > /dev/null
+make -s > /dev/null 2>&1
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC "$@" -c $src -o $out/fused_$name.o
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libimhd_$name.so imhd_api.o imhd_granular.o $out/fused_$name.o imhd_stability.o imhd_slabs.o imhd_h5.o -lcudart -ldl
 rm -f $out/fused_$name.o
