@@ -37,3 +37,5 @@ int imhd_init_ic_slab(int ic, float* Q, float a, float b, const float* x, const 
                       int nz_array, int kofs, void* stream);
 int imhd_init_axis_slab(float* g, float lo, float d, int n, int ofs, void* stream);
 int imhd_wall_leftright_planes(float* Q, int Nx, int Ny, int nz_array, int ka, int kb, void* stream);
+// internal entry point of imhd_fused.cu: imhd_qint_plane with blocks of block_rows x 32 threads
+int imhd_qint_plane_rows(const float* Q, float* out_plane, int k, const imhd_slab* s, int block_rows, void* stream);

@@ -35,6 +35,7 @@
 #include <vector>
 
 #include "imhd_common.cuh"
+#include "imhd_engine.h"
 
 namespace imhd {
 
@@ -1528,18 +1529,24 @@ static int fill_args(FusedArgs& A, const float* Qin, float* Qout, const float* q
     return 0;
 }
 
-extern "C" int imhd_qint_plane(const float* Q, float* out_plane, int k, const imhd_slab* s, void* stream) {
+// block_rows: rows of 32 threads per block.  8 by default; the slab engine asks for 4 (128 threads x 80 registers) so that the
+// blocks find room beside a resident block of the marching kernel instead of waiting for an SM of their own.
+int imhd_qint_plane_rows(const float* Q, float* out_plane, int k, const imhd_slab* s, int block_rows, void* stream) {
     FusedArgs A;
     if (int e = fill_args(A, Q, nullptr, nullptr, nullptr, nullptr, s)) return e;
     if (k < 0 || k > s->Nz - 2 || k < A.kmin || k + 1 > A.kmax) {
         set_error("imhd_qint_plane: plane %d not computable from array planes [%d,%d]", k, A.kmin, A.kmax);
         return IMHD_E_INVALID;
     }
-    const dim3 grid((s->Ny + 31) / 32, (s->Nx + 7) / 8), block(32, 8);
+    const dim3 grid((s->Ny + 31) / 32, (s->Nx + block_rows - 1) / block_rows), block(32, block_rows);
     if (s->path == IMHD_PATH_A) k_qint_plane<IMHD_PATH_A><<<grid, block, 0, (cudaStream_t)stream>>>(A, k, out_plane);
     else                        k_qint_plane<IMHD_PATH_B><<<grid, block, 0, (cudaStream_t)stream>>>(A, k, out_plane);
     IMHD_LAUNCH_CHECK(1);
     return 0;
+}
+
+extern "C" int imhd_qint_plane(const float* Q, float* out_plane, int k, const imhd_slab* s, void* stream) {
+    return imhd_qint_plane_rows(Q, out_plane, k, s, 8, stream);
 }
 
 extern "C" float imhd_wall_energy_fixed_point(float e, int max_iter) {

@@ -21,7 +21,11 @@
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2): a single-GPU user needs no NCCL, and inside a Python process
 // that has imported torch the already-loaded copy is reused instead of a second one.
+#include <cuda.h>
 #include <dlfcn.h>
+#include <unistd.h>
+#include <cstdlib>
+#include <cstring>
 #include <nccl.h>
 
 #include <vector>
@@ -109,17 +113,28 @@ struct SlabDev {
     int dev, rank, k0, nzl;
     float* Q[2];              // (8, nzl+2, Nx, Ny): array plane 0 is global plane k0-1
     float *gx, *gy, *gz;      // gz: the array's own planes (nzl+2 entries)
-    float* planes;            // [2 sets][lo, hi, up, down] + send_up, send_down, recv_lo, recv_hi, each (8,Nx,Ny)
+    float* planes;            // [2 sets][lo, hi, up, down] + send_up, send_down, 2 x (recv_lo, recv_hi), each (8,Nx,Ny)
     float* scratch;           // 16 floats (corner energy broadcast, stability rows)
-    cudaStream_t main, side;
-    cudaEvent_t ev_edges, ev_comm;
+    cudaStream_t main, side, ends;   // ends: highest priority -- the slab-end launch runs beside the interior launch, its blocks first
+    cudaEvent_t ev_edges, ev_comm, ev_fork;
     ncclComm_t comm;
+    // direct exchange: the neighbours' `planes` allocations as this process sees them ([0] the slab above, [1] the slab below)
+    float* peer[2];
+    bool peer_ipc[2];          // mapped with cudaIpcOpenMemHandle (closed on destroy)
+    unsigned seq;              // exchanges posted so far: the value the arrival counters reach
     imhd_slab desc;
     float* set(int which, int idx, size_t pl8) const { return planes + ((size_t)which * 4 + idx) * pl8; }
     float* stage(int idx, size_t pl8) const { return planes + (8 + (size_t)idx) * pl8; }
+    // four 32-bit words behind the fourteen planes: [0] / [1] arrival counters of the up-going / down-going message (written by
+    // the slab below / above), [2] the sequence number this slab publishes
+    static size_t words_at(size_t pl8) { return 14 * pl8; }
 };
+constexpr size_t kPlanesTail = 64;   // floats
 enum { P_LO = 0, P_HI = 1, P_UP = 2, P_DOWN = 3 };
+// the receive staging planes are double buffered by the parity of the exchange count: a neighbour that is one exchange ahead
+// (it may post exchange n + 1 as soon as this slab has POSTED n, before this slab has unpacked n) writes the other pair
 enum { S_SEND_UP = 0, S_SEND_DOWN = 1, S_RECV_LO = 2, S_RECV_HI = 3 };
+static int recv_stage(int idx, unsigned seq) { return idx + 2 * (int)(seq & 1u); }
 
 struct Engine {
     int Nx, Ny, Nz, world;
@@ -127,7 +142,8 @@ struct Engine {
     std::vector<SlabDev> s;
     NcclApi* nccl;
     int cur, qcur, path;
-    bool q_ready, primed, have_grids, overlap;
+    bool q_ready, primed, have_grids, overlap, ends_concurrent;
+    bool direct;               // plane exchange by the copy engines into the neighbours' buffers (else ncclSend / ncclRecv)
     float D, dt, dx, dy, dz, corner_e;
     float bounds[6];
 };
@@ -142,15 +158,154 @@ void eng_destroy(Engine* e) {
         cudaSetDevice(sl.dev);
         if (sl.main) cudaStreamSynchronize(sl.main);
         if (sl.side) cudaStreamSynchronize(sl.side);
+        if (sl.ends) cudaStreamSynchronize(sl.ends);
+        for (int d = 0; d < 2; ++d)
+            if (sl.peer_ipc[d] && sl.peer[d]) cudaIpcCloseMemHandle(sl.peer[d]);
         if (sl.comm && e->nccl) e->nccl->CommDestroy(sl.comm);
         cudaFree(sl.Q[0]); cudaFree(sl.Q[1]); cudaFree(sl.gx); cudaFree(sl.gy); cudaFree(sl.gz);
         cudaFree(sl.planes); cudaFree(sl.scratch);
         if (sl.ev_edges) cudaEventDestroy(sl.ev_edges);
         if (sl.ev_comm) cudaEventDestroy(sl.ev_comm);
+        if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
+        if (sl.ends) cudaStreamDestroy(sl.ends);
         if (sl.main) cudaStreamDestroy(sl.main);
         if (sl.side) cudaStreamDestroy(sl.side);
     }
     delete e;
+}
+
+// ---- direct plane exchange ------------------------------------------------------------------------------------------
+// ncclSend / ncclRecv run as kernels of their own (one 512+-thread block per channel): they need whole SMs, and the interior
+// launch under which the exchange is meant to hide holds every SM with one 8-warp block for a third of the step -- the NCCL
+// kernels wait for the first blocks to retire and then delay the blocks behind them (measured on 2 B200: 1.608 ms per step
+// against 1.480 ms with the exchange switched off, and 1.81 ms with NCCL held to one or two channels).  So the planes travel
+// by the COPY ENGINES instead: a slab writes its packed plane straight into the neighbour's receive buffer over NVLink
+// (cudaMemcpyAsync to the peer's allocation -- mapped with CUDA IPC when the neighbour is another process, used as it is
+// when it is a slab of this process), then a 32-bit sequence number into the neighbour's arrival counter (a second copy on
+// the same stream: ordered behind the data), and the receiving stream waits for its counter with cuStreamWaitValue32.  No
+// SM is involved; pack / unpack / predictor-plane kernels are small enough to be co-resident with a marching block.
+// The buffer discipline is the one the NCCL path has: every slab waits for BOTH neighbours' planes of exchange n before it
+// posts exchange n + 1, and a receive buffer is only rewritten two exchanges of the same kind later.
+// NCCL stays for the set-up (handle all-gather), the corner-energy broadcast and the CFL all-gather, and as the fallback
+// (another node, no peer access, IMHD_SLAB_EXCHANGE=nccl).
+typedef CUresult (*StreamValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+struct StreamOps { StreamValue32Fn wait = nullptr, write = nullptr; };
+static StreamOps* stream_ops() {
+    static StreamOps ops;
+    static int state = 0;
+    if (state == 0) {
+        state = -1;
+        void *w = nullptr, *r = nullptr;
+        cudaDriverEntryPointQueryResult q1, q2;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &w, cudaEnableDefault, &q1) == cudaSuccess && q1 == cudaDriverEntryPointSuccess &&
+            cudaGetDriverEntryPoint("cuStreamWriteValue32", &r, cudaEnableDefault, &q2) == cudaSuccess && q2 == cudaDriverEntryPointSuccess && w && r) {
+            ops.wait = (StreamValue32Fn)w;
+            ops.write = (StreamValue32Fn)r;
+            state = 1;
+        }
+        cudaGetLastError();
+    }
+    return state == 1 ? &ops : nullptr;
+}
+
+static SlabDev* local_slab(Engine* e, int rank) {
+    for (SlabDev& sl : e->s)
+        if (sl.rank == rank) return &sl;
+    return nullptr;
+}
+
+// Collective over all slabs of the domain: maps the neighbours' buffers; e->direct ends up true on every slab or on none.
+static int setup_direct(Engine* e) {
+    e->direct = false;
+    NcclApi* n = e->nccl;
+    const int nl = (int)e->s.size(), W = e->world;
+    const char* mode = getenv("IMHD_SLAB_EXCHANGE");
+    int want = !(mode && strcmp(mode, "nccl") == 0) && stream_ops() != nullptr;
+    // one row per slab: [0] ok so far, [1..16] the IPC handle of its `planes` allocation (64 bytes), [17] process id
+    constexpr int ROW = 20;
+    std::vector<int> mine((size_t)nl * ROW, 0), all((size_t)nl * W * ROW, 0);
+    for (int q = 0; q < nl; ++q) {
+        SlabDev& sl = e->s[q];
+        ENG_DEV(sl);
+        int* row = &mine[(size_t)q * ROW];
+        cudaIpcMemHandle_t h;
+        static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+        row[0] = want && cudaIpcGetMemHandle(&h, sl.planes) == cudaSuccess;
+        if (row[0]) memcpy(row + 1, &h, sizeof(h));
+        row[17] = (int)getpid();
+        cudaGetLastError();
+    }
+    auto gather = [&]() -> int {   // row q of every local slab -> all rows, on every slab
+        std::vector<int*> dsend(nl, nullptr), drecv(nl, nullptr);
+        for (int q = 0; q < nl; ++q) {
+            SlabDev& sl = e->s[q];
+            ENG_DEV(sl);
+            IMHD_CUDA(cudaMalloc(&dsend[q], sizeof(int) * ROW));
+            IMHD_CUDA(cudaMalloc(&drecv[q], sizeof(int) * ROW * W));
+            IMHD_CUDA(cudaMemcpyAsync(dsend[q], &mine[(size_t)q * ROW], sizeof(int) * ROW, cudaMemcpyHostToDevice, sl.main));
+        }
+        IMHD_NCCL(n->GroupStart());
+        for (int q = 0; q < nl; ++q) {
+            cudaSetDevice(e->s[q].dev);
+            IMHD_NCCL(n->AllGather(dsend[q], drecv[q], ROW, ncclInt, e->s[q].comm, e->s[q].main));
+        }
+        IMHD_NCCL(n->GroupEnd());
+        for (int q = 0; q < nl; ++q) {
+            SlabDev& sl = e->s[q];
+            ENG_DEV(sl);
+            IMHD_CUDA(cudaMemcpyAsync(&all[(size_t)q * W * ROW], drecv[q], sizeof(int) * ROW * W, cudaMemcpyDeviceToHost, sl.main));
+            IMHD_CUDA(cudaStreamSynchronize(sl.main));
+            cudaFree(dsend[q]); cudaFree(drecv[q]);
+        }
+        return 0;
+    };
+    if (int rc = gather()) return rc;
+    // map the two neighbours of every local slab
+    for (int q = 0; q < nl; ++q) {
+        SlabDev& sl = e->s[q];
+        ENG_DEV(sl);
+        const int* rows = &all[(size_t)q * W * ROW];
+        int ok = 1;
+        for (int r = 0; r < W; ++r) ok = ok && rows[(size_t)r * ROW];
+        const int nb[2] = {(sl.rank + 1) % W, (sl.rank + W - 1) % W};
+        for (int d = 0; d < 2 && ok; ++d) {
+            if (SlabDev* other = local_slab(e, nb[d])) {   // a slab of this process: its pointer as it is, peer access if the devices offer it
+                sl.peer[d] = other->planes;
+                int can = 0;
+                if (other->dev != sl.dev && cudaDeviceCanAccessPeer(&can, sl.dev, other->dev) == cudaSuccess && can) {
+                    const cudaError_t pe = cudaDeviceEnablePeerAccess(other->dev, 0);
+                    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+                }
+                cudaGetLastError();
+            } else if (d == 1 && nb[1] == nb[0] && sl.peer[0]) {   // two slabs in two processes: one neighbour, one mapping
+                sl.peer[1] = sl.peer[0];
+            } else {
+                cudaIpcMemHandle_t h;
+                memcpy(&h, rows + (size_t)nb[d] * ROW + 1, sizeof(h));
+                void* ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess && ptr) {
+                    sl.peer[d] = (float*)ptr;
+                    sl.peer_ipc[d] = true;
+                } else {
+                    cudaGetLastError();
+                    ok = 0;
+                }
+            }
+        }
+        mine[(size_t)q * ROW] = ok;
+    }
+    // second round: everybody mapped everything?
+    if (int rc = gather()) return rc;
+    int ok = 1;
+    for (int r = 0; r < W; ++r) ok = ok && all[(size_t)r * ROW];
+    e->direct = ok != 0;
+    if (!e->direct)
+        for (SlabDev& sl : e->s)
+            for (int d = 0; d < 2; ++d) {
+                if (sl.peer_ipc[d] && sl.peer[d]) { cudaSetDevice(sl.dev); cudaIpcCloseMemHandle(sl.peer[d]); }
+                sl.peer[d] = nullptr; sl.peer_ipc[d] = false;
+            }
+    return 0;
 }
 
 Engine* eng_create(int Nx, int Ny, int Nz, int world, int nlocal, const int* ranks, const int* devices, const void* uid) {
@@ -187,13 +342,18 @@ Engine* eng_create(int Nx, int Ny, int Nz, int world, int nlocal, const int* ran
         sl.nzl = slab_k0(Nz, world, sl.rank + 1) - sl.k0;
         min_nzl = sl.nzl < min_nzl ? sl.nzl : min_nzl;
         const size_t qbytes = e->pl8 * (size_t)(sl.nzl + 2) * sizeof(float);
+        int prio_lo = 0, prio_hi = 0;
+        if (cudaSetDevice(sl.dev) == cudaSuccess) cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         ok = cudaSetDevice(sl.dev) == cudaSuccess && cudaMalloc(&sl.Q[0], qbytes) == cudaSuccess && cudaMalloc(&sl.Q[1], qbytes) == cudaSuccess &&
              cudaMalloc(&sl.gx, sizeof(float) * Nx) == cudaSuccess && cudaMalloc(&sl.gy, sizeof(float) * Ny) == cudaSuccess &&
              cudaMalloc(&sl.gz, sizeof(float) * (sl.nzl + 2)) == cudaSuccess &&
-             cudaMalloc(&sl.planes, 12 * e->pl8 * sizeof(float)) == cudaSuccess && cudaMalloc(&sl.scratch, 64 * sizeof(double)) == cudaSuccess &&
+             cudaMalloc(&sl.planes, (14 * e->pl8 + kPlanesTail) * sizeof(float)) == cudaSuccess &&
+             cudaMemset(sl.planes + 14 * e->pl8, 0, kPlanesTail * sizeof(float)) == cudaSuccess && cudaMalloc(&sl.scratch, 64 * sizeof(double)) == cudaSuccess &&
              cudaMemset(sl.Q[0], 0, qbytes) == cudaSuccess && cudaMemset(sl.Q[1], 0, qbytes) == cudaSuccess &&
              cudaStreamCreateWithFlags(&sl.main, cudaStreamNonBlocking) == cudaSuccess &&
              cudaStreamCreateWithFlags(&sl.side, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&sl.ends, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sl.ev_edges, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sl.ev_comm, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) cuda_fail(cudaGetLastError(), "slab engine allocation", __FILE__, __LINE__);
@@ -220,8 +380,13 @@ Engine* eng_create(int Nx, int Ny, int Nz, int world, int nlocal, const int* ran
         if (r != ncclSuccess) { nccl_fail(r, "communicator set-up"); ok = false; }
     }
     if (!ok) { eng_destroy(e); return nullptr; }
+    if (setup_direct(e) != 0) { eng_destroy(e); return nullptr; }
     // every slab of the domain has to take the same decision (min over all slabs: floor(Nz/world))
     e->overlap = Nz / world >= 2 * g_edge + 2;
+    {   // test / measurement hook: IMHD_SLAB_ENDS_CONCURRENT=0 puts the end launch in front of the interior launch on one stream
+        const char* v = getenv("IMHD_SLAB_ENDS_CONCURRENT");
+        e->ends_concurrent = !(v && v[0] == '0');
+    }
     (void)min_nzl;
     return e;
 }
@@ -343,8 +508,12 @@ int eng_set_spacing(Engine* e, float dx, float dy, float dz) {
 // ---- exchanges ---------------------------------------------------------------------------------------------------
 static cudaStream_t stream_of(SlabDev& sl, bool side) { return side ? sl.side : sl.main; }
 
-static int copy8(Engine* e, float* dst, long long dvs, const float* src, long long svs, cudaStream_t st) {
-    k_copy8<<<(unsigned)((e->plane + 255) / 256), 256, 0, st>>>(dst, dvs, src, svs, (long long)e->plane);
+// Kernels that run on the side stream under the interior launch use blocks small enough to fit into what a resident block of
+// the marching kernel AND its co-resident strip block leave of an SM (4608 registers), so they never wait for an SM of their
+// own (measured on 4 B200: the same step time as with 256-thread blocks -- kept because it cannot queue behind the strip).
+static int copy8(Engine* e, float* dst, long long dvs, const float* src, long long svs, cudaStream_t st, bool small = false) {
+    const unsigned threads = small ? 64 : 256;
+    k_copy8<<<(unsigned)((e->plane + threads - 1) / threads), threads, 0, st>>>(dst, dvs, src, svs, (long long)e->plane);
     IMHD_LAUNCH_CHECK(1);
     return 0;
 }
@@ -352,6 +521,33 @@ static int copy8(Engine* e, float* dst, long long dvs, const float* src, long lo
 // one ring exchange of a packed plane per direction, all local slabs in one NCCL group:
 //   send_up -> slab above (its recv_from_down), send_down -> slab below (its recv_from_up)
 static int ring_exchange(Engine* e, int i_send_up, int i_send_down, int i_recv_down, int i_recv_up, bool is_set, int which, bool side) {
+    for (SlabDev& sl : e->s) ++sl.seq;   // the same count on every slab of the domain: every exchange is collective
+    if (!is_set) {                       // staging planes: this exchange's receive pair
+        i_recv_down = recv_stage(i_recv_down, e->s[0].seq);
+        i_recv_up = recv_stage(i_recv_up, e->s[0].seq);
+    }
+    if (e->direct) {
+        StreamOps* ops = stream_ops();
+        const size_t bytes = e->pl8 * sizeof(float), words = SlabDev::words_at(e->pl8);
+        auto off = [&](int idx) { return is_set ? ((size_t)which * 4 + idx) * e->pl8 : (8 + (size_t)idx) * e->pl8; };   // as set() / stage()
+        for (SlabDev& sl : e->s) {   // post: plane, then sequence number, to either neighbour
+            ENG_DEV(sl);
+            cudaStream_t st = stream_of(sl, side);
+            const unsigned seq = sl.seq;
+            if (ops->write((CUstream)st, (CUdeviceptr)(sl.planes + words + 2), seq, 0) != CUDA_SUCCESS) { set_error("cuStreamWriteValue32 failed"); return IMHD_E_STATE; }
+            IMHD_CUDA(cudaMemcpyAsync(sl.peer[0] + off(i_recv_down), sl.planes + off(i_send_up), bytes, cudaMemcpyDefault, st));   // up-going
+            IMHD_CUDA(cudaMemcpyAsync(sl.peer[0] + words + 0, sl.planes + words + 2, sizeof(unsigned), cudaMemcpyDefault, st));
+            IMHD_CUDA(cudaMemcpyAsync(sl.peer[1] + off(i_recv_up), sl.planes + off(i_send_down), bytes, cudaMemcpyDefault, st));   // down-going
+            IMHD_CUDA(cudaMemcpyAsync(sl.peer[1] + words + 1, sl.planes + words + 2, sizeof(unsigned), cudaMemcpyDefault, st));
+        }
+        for (SlabDev& sl : e->s) {   // both neighbours' planes have landed
+            ENG_DEV(sl);
+            cudaStream_t st = stream_of(sl, side);
+            for (int w = 0; w < 2; ++w)
+                if (ops->wait((CUstream)st, (CUdeviceptr)(sl.planes + words + w), sl.seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed"); return IMHD_E_STATE; }
+        }
+        return 0;
+    }
     NcclApi* n = e->nccl;
     IMHD_NCCL(n->GroupStart());
     for (SlabDev& sl : e->s) {
@@ -376,21 +572,22 @@ static int exchange_ghosts(Engine* e, int qi, bool pbc, bool side) {
         ENG_DEV(sl);
         const long long vs = (long long)(sl.nzl + 2) * e->plane;
         cudaStream_t st = stream_of(sl, side);
-        if (int rc = copy8(e, sl.stage(S_SEND_UP, e->pl8), e->plane, sl.Q[qi] + (size_t)sl.nzl * e->plane, vs, st)) return rc;   // plane k1-1
-        if (int rc = copy8(e, sl.stage(S_SEND_DOWN, e->pl8), e->plane, sl.Q[qi] + e->plane, vs, st)) return rc;                  // plane k0
+        if (int rc = copy8(e, sl.stage(S_SEND_UP, e->pl8), e->plane, sl.Q[qi] + (size_t)sl.nzl * e->plane, vs, st, side)) return rc;   // plane k1-1
+        if (int rc = copy8(e, sl.stage(S_SEND_DOWN, e->pl8), e->plane, sl.Q[qi] + e->plane, vs, st, side)) return rc;                  // plane k0
     }
     if (int rc = ring_exchange(e, S_SEND_UP, S_SEND_DOWN, S_RECV_LO, S_RECV_HI, false, 0, side)) return rc;
     for (SlabDev& sl : e->s) {
         ENG_DEV(sl);
         const long long vs = (long long)(sl.nzl + 2) * e->plane;
         cudaStream_t st = stream_of(sl, side);
+        const float *rlo = sl.stage(recv_stage(S_RECV_LO, sl.seq), e->pl8), *rhi = sl.stage(recv_stage(S_RECV_HI, sl.seq), e->pl8);
         if (sl.rank > 0) {
-            if (int rc = copy8(e, sl.Q[qi], vs, sl.stage(S_RECV_LO, e->pl8), e->plane, st)) return rc;
+            if (int rc = copy8(e, sl.Q[qi], vs, rlo, e->plane, st, side)) return rc;
         } else if (pbc) {
-            if (int rc = copy8(e, sl.Q[qi] + e->plane, vs, sl.stage(S_RECV_LO, e->pl8), e->plane, st)) return rc;
+            if (int rc = copy8(e, sl.Q[qi] + e->plane, vs, rlo, e->plane, st, side)) return rc;
         }
         if (sl.rank < e->world - 1)
-            if (int rc = copy8(e, sl.Q[qi] + (size_t)(sl.nzl + 1) * e->plane, vs, sl.stage(S_RECV_HI, e->pl8), e->plane, st)) return rc;
+            if (int rc = copy8(e, sl.Q[qi] + (size_t)(sl.nzl + 1) * e->plane, vs, rhi, e->plane, st, side)) return rc;
     }
     return 0;
 }
@@ -403,8 +600,9 @@ static int exchange_qint(Engine* e, int qi, int which, bool side) {
         ENG_DEV(sl);
         cudaStream_t st = stream_of(sl, side);
         const int up_plane = sl.rank < e->world - 1 ? sl.k0 + sl.nzl - 1 : e->Nz - 2;
-        if (int rc = imhd_qint_plane(sl.Q[qi], sl.set(which, P_UP, e->pl8), up_plane, &sl.desc, st)) return rc;
-        if (int rc = imhd_qint_plane(sl.Q[qi], sl.set(which, P_DOWN, e->pl8), sl.k0, &sl.desc, st)) return rc;
+        const int rows = side ? 1 : 8;   // under the interior launch: one-warp blocks (80 registers) fit beside a marching block
+        if (int rc = imhd_qint_plane_rows(sl.Q[qi], sl.set(which, P_UP, e->pl8), up_plane, &sl.desc, rows, st)) return rc;
+        if (int rc = imhd_qint_plane_rows(sl.Q[qi], sl.set(which, P_DOWN, e->pl8), sl.k0, &sl.desc, rows, st)) return rc;
     }
     return ring_exchange(e, P_UP, P_DOWN, P_LO, P_HI, true, which, side);
 }
@@ -489,10 +687,19 @@ int eng_step(Engine* e, int nsteps) {
             // both ends hold E planes of the marching kernel (plane 0, and plane Nz-1 of path B, have kernels of their own and
             // do not count): equal ranges go out as ONE launch
             const int e0 = k0 + E + (k0 == 0 ? 1 : 0), e1 = k1 - E - (k1 == e->Nz && e->path == IMHD_PATH_B ? 1 : 0);
-            if (int rc = imhd_step_fused_ends(sl.Q[in], sl.Q[out], lo, hi, wrap, &sl.desc, k0, e0, e1, k1, sl.main)) return rc;
-            IMHD_CUDA(cudaEventRecord(sl.ev_edges, sl.main));
+            // The end launch and the interior launch are independent (both read the old state and write disjoint planes):
+            // the ends go to a stream of the highest priority forked off the main stream, so the two launches are runnable
+            // together, the block scheduler places the end blocks first and fills every SM they leave with interior blocks
+            // -- no drain / fill between the launches, no partial last wave of end blocks.
+            cudaStream_t es = e->ends_concurrent ? sl.ends : sl.main;
+            if (e->ends_concurrent) {
+                IMHD_CUDA(cudaEventRecord(sl.ev_fork, sl.main));
+                IMHD_CUDA(cudaStreamWaitEvent(sl.ends, sl.ev_fork, 0));
+            }
+            if (int rc = imhd_step_fused_ends(sl.Q[in], sl.Q[out], lo, hi, wrap, &sl.desc, k0, e0, e1, k1, es)) return rc;
+            IMHD_CUDA(cudaEventRecord(sl.ev_edges, es));
             if (int rc = imhd_step_fused_planes(sl.Q[in], sl.Q[out], lo, hi, wrap, &sl.desc, e0, e1, sl.main)) return rc;
-            IMHD_CUDA(cudaStreamWaitEvent(sl.side, sl.ev_edges, 0));
+            IMHD_CUDA(cudaStreamWaitEvent(sl.side, sl.ev_edges, 0));   // (the main stream follows the side stream below)
         }
         if (!e->overlap) {
             if (int rc = exchange_ghosts(e, out, e->path == IMHD_PATH_A, false)) return rc;
