@@ -394,14 +394,16 @@ def main():
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         achieved = BYTES_PER_CELL_UPDATE * cells_launch / (fused_ms * 1e-3) / 1e9 if n_l.value else None
-        kern = f"k_fused_pair<PATH_{path_name},8> (+ k_fused_strip<PATH_{path_name}> for the columns beyond the last full tile; timed together)"
+        kern = (f"k_fused_split<PATH_B,8> (+ k_fused_wstrip<PATH_B> for the columns beyond the last full tile, co-resident under it on a side "
+                f"stream; one event pair around both)" if path_name == "B" else
+                f"k_fused_pair<PATH_A,4,3> (+ k_fused_wstrip<PATH_A> for the columns beyond the last full tile; timed together)")
         line = {
             "metric": "cell_updates_per_sec", "value": value, "unit": "GLUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.workload == "strong" else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "finite": finite,
-            "host_loop": "C++ (libimhd_b200.so: imhd_ctx_step" + ("" if world == 1 else ", z-slab engine, ncclSend/Recv on a side stream") + ")",
+            "host_loop": "C++ (libimhd_b200.so: imhd_ctx_step" + ("" if world == 1 else ", z-slab engine, planes exchanged by the copy engines (CUDA IPC) on a side stream; IMHD_SLAB_EXCHANGE=nccl: ncclSend/Recv") + ")",
             "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_cell_update": BYTES_PER_CELL_UPDATE,

@@ -138,8 +138,9 @@ int imhd_step_fused(const float* Qin, float* Qout, const float* qint_lo, const f
 int imhd_step_fused_planes(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
                            const float* qint_wrap, const imhd_slab* s, int kfrom, int kto, void* stream);
 
-/* ... restricted to TWO plane ranges, [kfrom, kmid1) and [kmid2, kto), in ONE launch of the marching kernel: both slab
- * ends at once (a launch over a few planes of one end fills 1.5 waves of thread blocks, both ends fill three). */
+/* ... restricted to TWO plane ranges, [kfrom, kmid1) and [kmid2, kto): both slab ends at once.  ONE launch of the
+ * marching kernel when the two ranges hold the same number (<= 32) of its planes (plane 0, and plane Nz-1 of the
+ * diffusion pipeline, have kernels of their own and do not count), otherwise two launches; the same bits either way. */
 int imhd_step_fused_ends(const float* Qin, float* Qout, const float* qint_lo, const float* qint_hi,
                          const float* qint_wrap, const imhd_slab* s, int kfrom, int kmid1, int kmid2, int kto, void* stream);
 
@@ -172,7 +173,8 @@ float imhd_wall_energy_fixed_point(float e, int max_iter);
 
 /* Test hooks: force the z-chunk length of the fused kernel (0 = automatic); kernel-variant flags: bit 0 forces the
  * plain-load variant instead of the TMA one, bit 1 disables the remainder-strip kernel, bit 2 uses it even for
- * plane ranges shorter than 64, bit 8 selects the block-per-tile strip kernel instead of the warp-autonomous one, bits 4..7
+ * plane ranges shorter than 64, bit 3 keeps the strip and the two z faces of path B on the caller's stream instead of
+ * running them under the marching kernel on the library's side stream, bit 8 selects the block-per-tile strip kernel instead of the warp-autonomous one, bits 4..7
  * select the marching kernel (0 default, 1 one row per thread, 2 two rows per thread behind a block-wide barrier per plane,
  * 4 two rows per thread with the split-phase exchange barrier on both pipelines).  All give the same bits. */
 void imhd_set_chunk(int planes);

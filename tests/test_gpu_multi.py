@@ -112,3 +112,21 @@ def test_driver_with_two_gpus_writes_the_same_files(tmp_path, ngpu):
     assert files == sorted(os.listdir(outs[1])) and "fluidvars_8.h5" in files and "grid.h5" in files
     for f in files:
         assert filecmp.cmp(outs[0] + f, outs[1] + f, shallow=False), f
+
+
+def test_slab_engine_one_process_per_slab(ngpu):
+    """imhd_create_slab, the engine bench.py runs at N > 1: one process per GPU under torchrun, planes exchanged by the copy
+    engines through CUDA IPC mappings (and, second run, over ncclSend / ncclRecv): the single-GPU bits, both pipelines."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = min(ngpu, 4)
+    for mode in ("direct", "nccl"):
+        env = dict(os.environ, IMHD_SLAB_EXCHANGE=mode)
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                            "--master-port", "29533", os.path.join(root, "tools", "check_slab_engine.py")],
+                           capture_output=True, text=True, timeout=300, env=env, cwd=root)
+        assert r.returncode == 0, (mode, r.stdout[-2000:], r.stderr[-2000:])
+        assert r.stdout.count("bit-identical = True") == 6, (mode, r.stdout)
