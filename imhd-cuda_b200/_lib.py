@@ -59,6 +59,8 @@ SIGNATURES = {
     "imhd_step_fused_ends": (_i, [_p, _p, _p, _p, _p, C.POINTER(Slab), _i, _i, _i, _i, _p]),
     "imhd_stability_scan": (_i, [_p, C.POINTER(Slab), C.POINTER(Stability), _p]),
     "imhd_ctx_stability": (_i, [_p, _f, C.POINTER(Stability)]),
+    "imhd_ctx_step_adaptive": (_i, [_p, _i, _i, _f, _f, _p]),
+    "imhd_ctx_set_dt": (_i, [_p, _f]),
     "imhd_wall_energy_fixed_point": (_f, [_f, _i]),
     "imhd_set_chunk": (None, [_i]),
     "imhd_set_kernel_variant": (None, [_i]),

@@ -72,6 +72,9 @@ struct imhd_ctx {
     bool stop;
     int write_errors;
     char write_error_text[256];  // the writer thread's last error (its set_error is thread-local)
+    // ---- adaptive time step (imhd_ctx_step_adaptive): two scans in flight at most ----
+    unsigned long long* scan_pinned;   // 2 x 2 words of pinned host memory
+    cudaEvent_t scan_done[2];
 };
 
 extern "C" int imhd_abi_version(void) { return 1; }
@@ -162,6 +165,7 @@ extern "C" void imhd_destroy(imhd_ctx* c) {
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     cudaFree(c->buf[0]); cudaFree(c->buf[1]);
     cudaFree(c->gx); cudaFree(c->gy); cudaFree(c->gz); cudaFree(c->qint_planes);
+    if (c->scan_pinned) { cudaFreeHost(c->scan_pinned); cudaEventDestroy(c->scan_done[0]); cudaEventDestroy(c->scan_done[1]); }
     if (c->writer) {
         { std::lock_guard<std::mutex> g(*c->mu); c->stop = true; }
         c->cv->notify_all();
@@ -446,6 +450,67 @@ extern "C" int imhd_ctx_step(imhd_ctx* c, int nsteps) {
     }
     c->qint_valid = false;
     return 0;
+}
+
+extern "C" int imhd_ctx_set_dt(imhd_ctx* c, float dt) {
+    CTX_CHECK(c);
+    if (!(dt > 0.f)) { set_error("imhd_ctx_set_dt: dt = %g", (double)dt); return IMHD_E_INVALID; }
+    NOT_ON_SLABS(c, "imhd_ctx_set_dt");
+    c->dt = dt;
+    return 0;
+}
+
+// Adaptive time step without stalling the time loop.  Every `every` steps the CFL scan of the current state is queued behind
+// the step that produced it (kernel + 16-byte D2H into pinned memory + an event); its result decides the dt of the group of
+// steps that starts `every` steps LATER: the host only ever waits for a scan the device passed a whole group of steps ago, so
+// the device always has `every` steps queued (the reference's README lists the CFL-driven dt as a TODO; its scanner is a
+// forked host program run once, src/on-device/utils/compute_stability.cpp).
+extern "C" int imhd_ctx_step_adaptive(imhd_ctx* c, int nsteps, int every, float cfl_target, float dt_max, float* dt_used) {
+    CTX_CHECK(c);
+    NOT_ON_SLABS(c, "imhd_ctx_step_adaptive");
+    if (!c->primed) { set_error("imhd_ctx_step_adaptive before imhd_ctx_prime"); return IMHD_E_STATE; }
+    if (every < 2 || !(cfl_target > 0.f) || !(dt_max > 0.f) || nsteps < 0) {
+        set_error("imhd_ctx_step_adaptive: every = %d (>= 2), cfl_target = %g (> 0), dt_max = %g (> 0)", every, (double)cfl_target, (double)dt_max);
+        return IMHD_E_INVALID;
+    }
+    if (!c->scan_pinned) {
+        IMHD_CUDA(cudaMallocHost(&c->scan_pinned, 4 * sizeof(unsigned long long)));
+        IMHD_CUDA(cudaEventCreateWithFlags(&c->scan_done[0], cudaEventDisableTiming));
+        IMHD_CUDA(cudaEventCreateWithFlags(&c->scan_done[1], cudaEventDisableTiming));
+    }
+    imhd_slab s;
+    memset(&s, 0, sizeof(s));
+    s.Nx = c->Nx; s.Ny = c->Ny; s.Nz = c->Nz; s.k0 = 0; s.nzl = c->Nz; s.ghosts = 0;
+    s.dx = c->dx; s.dy = c->dy; s.dz = c->dz;
+    bool pending[2] = {false, false};
+    float dt_scan[2] = {0.f, 0.f};
+    int rc = 0;
+    for (int it = 0; it < nsteps && rc == 0; ++it) {
+        if (it % every == 0) {
+            const int slot = (it / every) & 1, prev = 1 - slot;
+            if (pending[prev]) {   // the scan taken `every` steps ago: the device passed it a group of steps ago
+                IMHD_CUDA(cudaEventSynchronize(c->scan_done[prev]));
+                pending[prev] = false;
+                imhd_stability r;
+                s.dt = dt_scan[prev];
+                imhd_stability_decode(c->scan_pinned + 2 * prev, &s, &r);
+                if (r.max_lhs > 0.f) {   // LHS is linear in dt: this dt puts the largest LHS of that state at cfl_target
+                    const float dt_new = cfl_target * dt_scan[prev] / r.max_lhs;
+                    c->dt = dt_new < dt_max ? dt_new : dt_max;
+                }
+            }
+            s.dt = c->dt;
+            if ((rc = imhd_stability_scan_async(c->buf[c->cur], &s, c->scan_pinned + 2 * slot, c->stream)) != 0) break;
+            IMHD_CUDA(cudaEventRecord(c->scan_done[slot], c->stream));
+            pending[slot] = true;
+            dt_scan[slot] = c->dt;
+        }
+        if (dt_used) dt_used[it] = c->dt;
+        rc = imhd_ctx_step(c, 1);
+    }
+    for (int q = 0; q < 2; ++q)   // nothing of this call writes into the pinned words after it returns
+        if (pending[q]) cudaEventSynchronize(c->scan_done[q]);
+    return rc;
 }
 
 extern "C" int imhd_ctx_get_state(imhd_ctx* c, float* host_Q) {

@@ -39,3 +39,6 @@ int imhd_init_axis_slab(float* g, float lo, float d, int n, int ofs, void* strea
 int imhd_wall_leftright_planes(float* Q, int Nx, int Ny, int nz_array, int ka, int kb, void* stream);
 // internal entry point of imhd_fused.cu: imhd_qint_plane with blocks of block_rows x 32 threads
 int imhd_qint_plane_rows(const float* Q, float* out_plane, int k, const imhd_slab* s, int block_rows, void* stream);
+// internal entry points of imhd_stability.cu: the scan without its stream synchronisation, and the decoder of its 16 bytes
+int imhd_stability_scan_async(const float* Q, const imhd_slab* s, unsigned long long h[2], void* stream);
+void imhd_stability_decode(const unsigned long long h[2], const imhd_slab* s, imhd_stability* host_out);

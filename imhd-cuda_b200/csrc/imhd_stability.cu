@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include "imhd_common.cuh"
+#include "imhd_engine.h"
 
 namespace imhd {
 
@@ -300,8 +301,9 @@ using namespace imhd;
 static int g_mode = IMHD_STABILITY_WAVE_SPEEDS;
 extern "C" void imhd_stability_mode(int mode) { g_mode = mode == IMHD_STABILITY_REFERENCE_QUIRKS ? mode : IMHD_STABILITY_WAVE_SPEEDS; }
 
-extern "C" int imhd_stability_scan(const float* Q, const imhd_slab* s, imhd_stability* host_out, void* stream) {
-    if (!Q || !s || !host_out) { set_error("imhd_stability_scan: null argument"); return IMHD_E_INVALID; }
+// The scan without the wait: kernel + 16-byte D2H into `h` (pinned memory if the caller wants to go on) on `stream`.
+int imhd_stability_scan_async(const float* Q, const imhd_slab* s, unsigned long long h[2], void* stream) {
+    if (!Q || !s || !h) { set_error("imhd_stability_scan: null argument"); return IMHD_E_INVALID; }
     if (int e = bad_dims(s->Nx, s->Ny, s->Nz)) return e;
     if (s->nzl < 1 || s->k0 < 0 || s->k0 + s->nzl > s->Nz || s->ghosts < 0) {
         set_error("imhd_stability_scan: slab [%d,%d) outside 0..%d", s->k0, s->k0 + s->nzl, s->Nz);
@@ -342,10 +344,14 @@ extern "C" int imhd_stability_scan(const float* Q, const imhd_slab* s, imhd_stab
         k_stability<1, false><<<grid, 256, 0, st>>>(Q, vs, first, ncells, tx, ty, tz, d_out);
     }
     IMHD_LAUNCH_CHECK(1);
-    unsigned long long h[2] = {0, 0};
-    IMHD_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, st));
+    IMHD_CUDA(cudaMemcpyAsync(h, d_out, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     IMHD_CUDA(cudaFreeAsync(d_out, st));
-    IMHD_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// The report of a finished scan (h as written by imhd_stability_scan_async, after its stream has passed the copy).
+void imhd_stability_decode(const unsigned long long h[2], const imhd_slab* s, imhd_stability* host_out) {
+    const long long plane = (long long)s->Nx * s->Ny;
     const unsigned bits = (unsigned)(h[0] >> 32);
     const long long cell = h[0] ? (long long)(0xFFFFFFFFu - (unsigned)(h[0] & 0xFFFFFFFFu)) : 0;
     float mx;
@@ -356,5 +362,13 @@ extern "C" int imhd_stability_scan(const float* Q, const imhd_slab* s, imhd_stab
     host_out->j = (int)(cell % s->Ny);
     host_out->violations = h[1];
     host_out->dt_new = h[0] ? 0.1f * s->dt / mx : 0.0f;  // alpha = 0.1 (compute_stability.cpp:139-141)
+}
+
+extern "C" int imhd_stability_scan(const float* Q, const imhd_slab* s, imhd_stability* host_out, void* stream) {
+    if (!host_out) { set_error("imhd_stability_scan: null argument"); return IMHD_E_INVALID; }
+    unsigned long long h[2] = {0, 0};
+    if (int e = imhd_stability_scan_async(Q, s, h, stream)) return e;
+    IMHD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    imhd_stability_decode(h, s, host_out);
     return 0;
 }

@@ -305,6 +305,16 @@ class Context:
         return {"max_lhs": out.max_lhs, "argmax_ijk": (out.i, out.j, out.k), "violations": int(out.violations),
                 "dt_new": out.dt_new}
 
+    def step_adaptive(self, nsteps: int, every: int = 10, cfl_target: float = 0.5, dt_max: float = 1e30) -> np.ndarray:
+        """nsteps fused steps with the time step following the CFL scan (imhd_ctx_step_adaptive: scanned every `every`
+        steps without stalling the loop, applied one group of steps later).  Returns the dt of every step."""
+        used = np.zeros(nsteps, np.float32)
+        check(self.L.imhd_ctx_step_adaptive(self.h, nsteps, every, cfl_target, dt_max, used.ctypes.data_as(C.c_void_p)))
+        return used
+
+    def set_dt(self, dt: float):
+        check(self.L.imhd_ctx_set_dt(self.h, dt))
+
     def set_state(self, Q: np.ndarray):
         Q = np.ascontiguousarray(Q, dtype=np.float32)
         assert Q.shape == self.shape

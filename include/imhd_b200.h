@@ -238,6 +238,17 @@ int imhd_ctx_get_state(imhd_ctx* ctx, float* host_Q);
 int imhd_ctx_get_grids(imhd_ctx* ctx, float* x, float* y, float* z);
 /* imhd_stability_scan of the context's current state with its spacing and the given dt. */
 int imhd_ctx_stability(imhd_ctx* ctx, float dt, imhd_stability* host_out);
+/* Adaptive time step on top of the scan (the reference's README keeps "adaptive dt" as a TODO; its scanner
+ * src/on-device/utils/compute_stability.cpp runs once, as a forked host program).  nsteps fused steps; before steps 0,
+ * every, 2*every, ... the current state is scanned on the context's stream WITHOUT stalling the loop, and the scan taken
+ * before step g*every sets the dt of steps [(g+1)*every, (g+2)*every):
+ *     dt = min(dt_max, cfl_target * dt_scan / max_lhs)      (LHS is linear in dt; dt_scan = the dt in use at the scan)
+ * -- one group of lag, so that the host only waits for results the device produced a whole group of steps earlier.  The
+ * first group runs with the context's dt; the context keeps the last dt.  dt_used (may be NULL) receives the dt of every
+ * step.  every >= 2.  Single-GPU contexts. */
+int imhd_ctx_step_adaptive(imhd_ctx* ctx, int nsteps, int every, float cfl_target, float dt_max, float* dt_used);
+/* Replace the time step set by imhd_ctx_prime (nothing else of the priming depends on it).  Single-GPU contexts. */
+int imhd_ctx_set_dt(imhd_ctx* ctx, float dt);
 /* Device pointer of the current state (valid until the next step call). */
 float* imhd_ctx_device_state(imhd_ctx* ctx);
 void* imhd_ctx_stream(imhd_ctx* ctx);

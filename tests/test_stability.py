@@ -208,3 +208,38 @@ def test_cuda_scan_of_slabs_combines_to_the_global_scan(imhd, torch, O, oracle_m
         assert c["max_lhs"] == whole["max_lhs"] and c["argmax_ijk"] == whole["argmax_ijk"]
         assert c["violations"] == whole["violations"]
         assert c["dt_new"] == pytest.approx(whole["dt_new"], rel=1e-6)
+
+
+@pytest.mark.gpu
+def test_adaptive_dt_loop_follows_the_scan_one_group_later(imhd):
+    """imhd_ctx_step_adaptive: the scan taken before step g*every decides the dt of steps [(g+1)*every, (g+2)*every) as
+    min(dt_max, cfl * dt_scan / max_lhs), the first group runs with the primed dt -- replayed here with synchronous scans and
+    imhd_ctx_set_dt on a second context: the same dt sequence (exactly) and the same bits."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    dims, every, nsteps, cfl, dt0, dt_max = (48, 40, 32), 3, 11, np.float32(0.4), np.float32(1e-4), np.float32(2e-3)
+    B = (-3.14159, 3.14159) * 3
+    for path, D in ((imhd.PATH_B, 0.01), (imhd.PATH_A, 0.0)):
+        with imhd.Context(*dims) as c:
+            c.init_grids(*B); c.init_screwpinch_stride(1.0); c.prime(path, D, float(dt0))
+            used = c.step_adaptive(nsteps, every=every, cfl_target=float(cfl), dt_max=float(dt_max))
+            Qa = c.get_state()
+        with imhd.Context(*dims) as r:
+            r.init_grids(*B); r.init_screwpinch_stride(1.0); r.prime(path, D, float(dt0))
+            dt, want, scans = dt0, [], []
+            for it in range(nsteps):
+                if it % every == 0:
+                    if it >= every:   # the scan of the group before decides this group
+                        dts, mx = scans[it // every - 1]
+                        if mx > 0:
+                            dt = min(np.float32(cfl * dts / np.float32(mx)), dt_max)
+                            r.set_dt(float(dt))
+                    scans.append((dt, r.stability(float(dt))["max_lhs"]))
+                want.append(dt)
+                r.step(1)
+            Qb = r.get_state()
+        assert np.array_equal(np.asarray(want, np.float32).view(np.uint32), used.view(np.uint32)), (path, want, used.tolist())
+        assert len(set(used.tolist())) > 1 and used.max() <= dt_max      # the loop did adapt
+        assert np.isfinite(Qa).all() and np.array_equal(Qa.view(np.uint32), Qb.view(np.uint32)), path
