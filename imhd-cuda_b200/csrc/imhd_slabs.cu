@@ -159,6 +159,10 @@ void eng_destroy(Engine* e) {
         if (sl.main) cudaStreamSynchronize(sl.main);
         if (sl.side) cudaStreamSynchronize(sl.side);
         if (sl.ends) cudaStreamSynchronize(sl.ends);
+        // teardown order: this slab's streams are idle (every plane a neighbour sent it has landed: its side stream waited
+        // for them), so the neighbours' buffers mapped here are no longer written -> unmap them, THEN leave the communicator,
+        // THEN free what this slab exported (an exporter should not free a region an importer still maps; every slab of the
+        // domain is destroyed collectively, like the communicator)
         for (int d = 0; d < 2; ++d)
             if (sl.peer_ipc[d] && sl.peer[d]) cudaIpcCloseMemHandle(sl.peer[d]);
         if (sl.comm && e->nccl) e->nccl->CommDestroy(sl.comm);
